@@ -1,0 +1,95 @@
+"""ctypes binding of libdnr_b200.so (include/dnr.h).  There is NO fallback: if the library is missing
+or a call fails, this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdnr_b200.so")
+
+FLAG_ACTIVATED, FLAG_ANTIALIASED, FLAG_NORMALS, FLAG_ACCUMULATE = 1, 2, 4, 8
+REC_FLOATS, REC_FLOATS_N, GRAD_FLOATS = 12, 16, 16
+DEPTH_LOSS_TYPES = {None: 0, "EdgeAwareLogL1": 1, "LogL1": 2, "L1": 3, "MSE": 4}
+
+_f, _i, _p = C.c_float, C.c_int32, C.c_void_p
+
+
+class DnrArgs(C.Structure):
+    """Field-for-field mirror of `struct DnrArgs` in include/dnr.h (tests/test_abi.py checks the order)."""
+
+    _fields_ = [
+        ("n_gauss", _i), ("width", _i), ("height", _i), ("tile_size", _i), ("sh_degree", _i), ("sh_bases", _i),
+        ("flags", C.c_uint32), ("reserved0", _i),
+        ("near_plane", _f), ("far_plane", _f), ("eps2d", _f), ("radius_clip", _f),
+        ("background", _f * 3), ("reserved1", _f),
+        ("n_isects", C.c_int64),
+        ("viewmat", _p), ("K", _p), ("c2w", _p),
+        ("means", _p), ("quats", _p), ("scales", _p), ("opacities", _p), ("sh_dc", _p), ("sh_rest", _p),
+        ("radii", _p), ("means2d", _p), ("depths", _p), ("conics", _p), ("opac_act", _p), ("compensations", _p),
+        ("colors", _p), ("normals_world", _p), ("tiles_per_gauss", _p), ("depth_keys", _p), ("records", _p),
+        ("ws_scan", _p), ("ws_sort", _p), ("flatten_ids", _p), ("tile_offsets", _p),
+        ("out_rgb", _p), ("out_depth", _p), ("out_alpha", _p), ("out_normal", _p), ("out_surface_normal", _p),
+        ("last_ids", _p), ("normal_norm", _p), ("clamp_mask", _p), ("depth_max", _p),
+        ("v_rgb", _p), ("v_depth", _p), ("v_normal", _p), ("v_alpha", _p), ("grad_records", _p),
+        ("v_means", _p), ("v_quats", _p), ("v_scales", _p), ("v_opacities", _p), ("v_sh_dc", _p), ("v_sh_rest", _p),
+        ("v_means2d", _p), ("v_means2d_abs", _p),
+        ("gt_depth", _p), ("gt_normal", _p), ("gt_rgb", _p), ("loss_partials", _p),
+        ("depth_lambda", _f), ("depth_tolerance", _f), ("depth_loss_type", _i), ("use_normal_loss", _i),
+        ("v_loss", _f), ("reserved2", _f),
+    ]
+
+
+POINTER_FIELDS = {n for n, t in DnrArgs._fields_ if t is _p}
+
+_lib: Optional[C.CDLL] = None
+
+
+class DnrError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Loads the shared library, failing loudly when it has not been built (python -m dn_splatter_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DnrError(
+            f"{LIB_PATH} is missing: build it with `python -m dn_splatter_b200.build` "
+            "(nvcc, sm_100a). dn_splatter_b200 has no CPU or PyTorch fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    A = C.POINTER(DnrArgs)
+    lib.dnr_version.restype = C.c_int
+    lib.dnr_error_string.restype = C.c_char_p
+    lib.dnr_error_string.argtypes = [C.c_int]
+    for name in ("dnr_project_fwd", "dnr_bin_sort", "dnr_raster_fwd", "dnr_finalize_fwd", "dnr_normal_from_depth",
+                 "dnr_raster_bwd", "dnr_project_bwd", "dnr_loss_fwd"):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [A, C.c_void_p]
+    lib.dnr_bin_scan.restype = C.c_int
+    lib.dnr_bin_scan.argtypes = [A, C.c_void_p, C.POINTER(C.c_int64)]
+    lib.dnr_loss_bwd.restype = C.c_int
+    lib.dnr_loss_bwd.argtypes = [A, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dnr_bin_scan_workspace_bytes.restype = C.c_size_t
+    lib.dnr_bin_scan_workspace_bytes.argtypes = [C.c_int32]
+    lib.dnr_bin_sort_workspace_bytes.restype = C.c_size_t
+    lib.dnr_bin_sort_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32]
+    _lib = lib
+    return lib
+
+
+EXPORTS = (
+    "dnr_version", "dnr_error_string", "dnr_project_fwd", "dnr_bin_scan_workspace_bytes", "dnr_bin_scan",
+    "dnr_bin_sort_workspace_bytes", "dnr_bin_sort", "dnr_raster_fwd", "dnr_finalize_fwd", "dnr_normal_from_depth",
+    "dnr_raster_bwd", "dnr_project_bwd", "dnr_loss_fwd", "dnr_loss_bwd",
+)
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().dnr_error_string(code).decode()
+        raise DnrError(f"{what} failed with code {code}: {msg}")

@@ -1,0 +1,217 @@
+// Tile binning: one binning shared by the colour/depth and the normal channels.
+//
+// Replaces gsplat isect_tiles + cub radix sort of 64-bit (tile|depth) keys + isect_offset_encode
+// (reference call sites /root/reference/dn_splatter/dn_model.py:495-516 and the second, redundant
+// binning hidden in the legacy rasterize_gaussians call at :564-575).
+//
+// B200-first formulation (same result, ~4x less sort traffic than sorting I 64-bit keys):
+//   1. sort the N Gaussians once by depth bits (32-bit keys, N items; culled = 0xFFFFFFFF go last);
+//      a stable sort keeps equal depths in ascending Gaussian index;
+//   2. exclusive-scan the tile counts in that depth order -> where each Gaussian emits;
+//   3. emit (tile_id, gaussian_id) pairs in depth order — one warp per Gaussian, coalesced;
+//   4. STABLE radix sort of the I pairs on the tile-id bits only (13-15 bits, 16-bit keys): within a
+//      tile the depth order of step 1 survives, so the list equals gsplat's sort by (tile, depth, id);
+//   5. tile offsets from the sorted tile ids.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct GatherCounts {
+  const int32_t* tiles_per_gauss;
+  const int32_t* order;
+  int32_t n;
+  __host__ __device__ __forceinline__ int64_t operator()(int32_t i) const {
+    return i < n ? (int64_t)tiles_per_gauss[order[i]] : (int64_t)0;
+  }
+};
+
+__global__ void iota_kernel(int32_t* out, int32_t n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+
+struct ScanWs {
+  uint32_t* keys_sorted;
+  int32_t* order;
+  int32_t* iota;
+  int64_t* isect_start;  // [N+1]
+  void* cub_temp;
+  size_t cub_bytes;
+  size_t total;
+};
+
+ScanWs carve_scan(void* base, int32_t n) {
+  ScanWs w;
+  size_t off = 0;
+  char* p = (char*)base;
+  w.keys_sorted = (uint32_t*)(p + off); off += align_up((size_t)n * 4);
+  w.order = (int32_t*)(p + off); off += align_up((size_t)n * 4);
+  w.iota = (int32_t*)(p + off); off += align_up((size_t)n * 4);
+  w.isect_start = (int64_t*)(p + off); off += align_up((size_t)(n + 1) * 8);
+  size_t sort_bytes = 0, scan_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, n, 0, 32);
+  GatherCounts f{nullptr, nullptr, n};
+  cub::TransformInputIterator<int64_t, GatherCounts, cub::CountingInputIterator<int32_t>> it(
+      cub::CountingInputIterator<int32_t>(0), f);
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, it, (int64_t*)nullptr, n + 1);
+  w.cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+  w.cub_temp = (void*)(p + off); off += align_up(w.cub_bytes);
+  w.total = off;
+  return w;
+}
+
+template <typename KeyT>
+struct SortWs {
+  KeyT* keys_in;
+  KeyT* keys_out;
+  int32_t* gids_in;
+  void* cub_temp;
+  size_t cub_bytes;
+  size_t total;
+};
+
+template <typename KeyT>
+SortWs<KeyT> carve_sort(void* base, int64_t n_isects, int tile_bits) {
+  SortWs<KeyT> w;
+  size_t off = 0;
+  char* p = (char*)base;
+  const size_t n = (size_t)(n_isects > 0 ? n_isects : 1);
+  w.keys_in = (KeyT*)(p + off); off += align_up(n * sizeof(KeyT));
+  w.keys_out = (KeyT*)(p + off); off += align_up(n * sizeof(KeyT));
+  w.gids_in = (int32_t*)(p + off); off += align_up(n * 4);
+  size_t sort_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const KeyT*)nullptr, (KeyT*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, (int64_t)n, 0, tile_bits);
+  w.cub_bytes = sort_bytes;
+  w.cub_temp = (void*)(p + off); off += align_up(sort_bytes);
+  w.total = off;
+  return w;
+}
+
+inline int tile_bits_for(int n_tiles) {
+  int b = 1;
+  while ((1 << b) < n_tiles) ++b;
+  return b;
+}
+
+// One warp per depth-sorted Gaussian; lanes stride over its tile box (row-major, as gsplat emits).
+template <typename KeyT>
+__global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_t* __restrict__ order,
+                                                  const int64_t* __restrict__ isect_start, KeyT* __restrict__ keys,
+                                                  int32_t* __restrict__ gids, int tiles_x, int tiles_y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= a.n_gauss) return;
+  const int64_t start = isect_start[warp];
+  const int count = (int)(isect_start[warp + 1] - start);
+  if (count == 0) return;
+  const int g = order[warp];
+  int x0, y0, x1, y1;
+  dnr_tile_box(a.means2d[g * 2 + 0], a.means2d[g * 2 + 1], a.radii[g], tiles_x, tiles_y, x0, y0, x1, y1);
+  const int nx = x1 - x0;
+  for (int k = lane; k < count; k += 32) {
+    const int ty = y0 + k / nx, tx = x0 + k % nx;
+    keys[start + k] = (KeyT)(ty * tiles_x + tx);
+    gids[start + k] = g;
+  }
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256) offsets_kernel(const KeyT* __restrict__ keys, int64_t n_isects, int n_tiles,
+                                                     int32_t* __restrict__ offsets) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_isects == 0) {
+    if (i <= n_tiles) offsets[i] = 0;
+    return;
+  }
+  if (i >= n_isects) return;
+  const int cur = (int)keys[i];
+  if (i == 0) {
+    for (int t = 0; t <= cur; ++t) offsets[t] = 0;
+  } else {
+    const int prev = (int)keys[i - 1];
+    for (int t = prev + 1; t <= cur; ++t) offsets[t] = (int32_t)i;
+  }
+  if (i == n_isects - 1) {
+    for (int t = cur + 1; t <= n_tiles; ++t) offsets[t] = (int32_t)n_isects;
+  }
+}
+
+template <typename KeyT>
+int bin_sort_impl(const DnrArgs* a, cudaStream_t s, int n_tiles, int tile_bits) {
+  const int tiles_x = dnr_tiles_x(a), tiles_y = dnr_tiles_y(a);
+  ScanWs sw = carve_scan(a->ws_scan, a->n_gauss);
+  SortWs<KeyT> w = carve_sort<KeyT>(a->ws_sort, a->n_isects, tile_bits);
+  const int64_t I = a->n_isects;
+  if (I > 0) {
+    const int64_t threads = (int64_t)a->n_gauss * 32;
+    emit_kernel<KeyT><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(*a, sw.order, sw.isect_start, w.keys_in, w.gids_in,
+                                                                          tiles_x, tiles_y);
+    DNR_CHECK_LAUNCH();
+    size_t bytes = w.cub_bytes;
+    DNR_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, bytes, (const KeyT*)w.keys_in, w.keys_out,
+                                             (const int32_t*)w.gids_in, a->flatten_ids, I, 0, tile_bits, s));
+  }
+  const int64_t n = I > 0 ? I : (int64_t)n_tiles + 1;
+  offsets_kernel<KeyT><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.keys_out, I, n_tiles, a->tile_offsets);
+  DNR_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t dnr_bin_scan_workspace_bytes(int32_t n_gauss) {
+  if (n_gauss <= 0) return 0;
+  return carve_scan(nullptr, n_gauss).total;
+}
+
+extern "C" int dnr_bin_scan(const DnrArgs* a, void* stream, int64_t* n_isects_host) {
+  if (!a || !n_isects_host) return DNR_E_NULL;
+  if (a->n_gauss <= 0) return DNR_E_SIZE;
+  if (!a->ws_scan || !a->depth_keys || !a->tiles_per_gauss) return DNR_E_NULL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int32_t n = a->n_gauss;
+  ScanWs w = carve_scan(a->ws_scan, n);
+  iota_kernel<<<(n + 255) / 256, 256, 0, s>>>(w.iota, n);
+  DNR_CHECK_LAUNCH();
+  size_t bytes = w.cub_bytes;
+  DNR_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, bytes, (const uint32_t*)a->depth_keys, w.keys_sorted,
+                                           (const int32_t*)w.iota, w.order, n, 0, 32, s));
+  GatherCounts f{a->tiles_per_gauss, w.order, n};
+  cub::TransformInputIterator<int64_t, GatherCounts, cub::CountingInputIterator<int32_t>> it(
+      cub::CountingInputIterator<int32_t>(0), f);
+  bytes = w.cub_bytes;
+  DNR_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, bytes, it, w.isect_start, n + 1, s));
+  int64_t total = 0;
+  DNR_CUDA(cudaMemcpyAsync(&total, w.isect_start + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  DNR_CUDA(cudaStreamSynchronize(s));
+  *n_isects_host = total;
+  if (total > 0x7FFFFFFFLL) return DNR_E_OVERFLOW;
+  return 0;
+}
+
+extern "C" size_t dnr_bin_sort_workspace_bytes(int32_t n_gauss, int64_t n_isects, int32_t n_tiles) {
+  (void)n_gauss;
+  if (n_isects < 0 || n_tiles <= 0) return 0;
+  const int bits = tile_bits_for(n_tiles);
+  if (n_tiles <= 65536) return carve_sort<uint16_t>(nullptr, n_isects, bits).total;
+  return carve_sort<uint32_t>(nullptr, n_isects, bits).total;
+}
+
+extern "C" int dnr_bin_sort(const DnrArgs* a, void* stream) {
+  if (!a) return DNR_E_NULL;
+  if (a->n_gauss <= 0 || a->n_isects < 0 || a->width <= 0 || a->height <= 0) return DNR_E_SIZE;
+  if (a->n_isects > 0x7FFFFFFFLL) return DNR_E_OVERFLOW;
+  if (!a->ws_scan || !a->ws_sort || !a->tile_offsets || !a->means2d || !a->radii) return DNR_E_NULL;
+  if (a->n_isects > 0 && !a->flatten_ids) return DNR_E_NULL;
+  const int n_tiles = dnr_tiles_x(a) * dnr_tiles_y(a);
+  const int bits = tile_bits_for(n_tiles);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_tiles <= 65536) return bin_sort_impl<uint16_t>(a, s, n_tiles, bits);
+  return bin_sort_impl<uint32_t>(a, s, n_tiles, bits);
+}

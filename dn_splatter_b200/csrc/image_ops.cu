@@ -1,0 +1,237 @@
+// Full-image stencils around the rasterizer, each one pass over HBM instead of the reference's chains of
+// torch element-wise kernels.  Compiled with -fmad=false (cheap kernels; keeps results close to torch's).
+//
+//   finalize_fwd          dn_model.py:534-537 depth fill with the global max  +  :589-603 surface normal
+//                         (utils/normal_utils.py:9-48, utils/camera_utils.py:70-144 with c2w = I)
+//   normal_from_depth     the same stencil for an arbitrary depth map (normal_supervision == "depth",
+//                         dn_model.py:669-686)
+//   loss_fwd / loss_bwd   DNRegularization depth + normal terms (regularization_strategy.py:146-193;
+//                         losses.py:155-224 L1/LogL1/EdgeAwareLogL1, :279-295 TVLoss)
+#include "common.cuh"
+
+namespace {
+
+struct Intr { float fx, fy, cx, cy; };
+
+__device__ __forceinline__ Intr load_intr(const float* K) {
+  Intr k;
+  k.fx = __ldg(K + 0); k.fy = __ldg(K + 4); k.cx = __ldg(K + 2); k.cy = __ldg(K + 5);
+  return k;
+}
+
+__device__ __forceinline__ void backproject(const Intr& k, int u, int v, float d, float p[3]) {
+  p[0] = (((float)u + 0.5f) - k.cx) * d / k.fx;
+  p[1] = (((float)v + 0.5f) - k.cy) * d / k.fy;
+  p[2] = d;
+}
+
+// normal at interior pixel (i,j) from the 4-neighbourhood; `depth_at` returns the (filled) depth.
+template <typename F>
+__device__ __forceinline__ void stencil_normal(const Intr& k, int i, int j, F depth_at, float n[3]) {
+  float r[3], l[3], t[3], b[3];
+  backproject(k, j + 1, i, depth_at(i, j + 1), r);
+  backproject(k, j - 1, i, depth_at(i, j - 1), l);
+  backproject(k, j, i - 1, depth_at(i - 1, j), t);
+  backproject(k, j, i + 1, depth_at(i + 1, j), b);
+  const float a0 = r[0] - l[0], a1 = r[1] - l[1], a2 = r[2] - l[2];  // left -> right
+  const float c0 = t[0] - b[0], c1 = t[1] - b[1], c2 = t[2] - b[2];  // bottom -> top
+  n[0] = a1 * c2 - a2 * c1;
+  n[1] = a2 * c0 - a0 * c2;
+  n[2] = a0 * c1 - a1 * c0;
+  const float nn = fmaxf(sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]), 1e-12f);
+  n[0] /= nn; n[1] /= nn; n[2] /= nn;
+}
+
+__global__ void __launch_bounds__(256) finalize_fwd_kernel(const DnrArgs a) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (i >= a.height || j >= a.width) return;
+  const float maxd = __int_as_float(*a.depth_max);
+  const int W = a.width, H = a.height;
+  auto depth_at = [&](int y, int x) -> float {
+    const int p = y * W + x;
+    return a.out_alpha[p] > 0.f ? a.out_depth[p] : maxd;
+  };
+  const int pix = i * W + j;
+  if (!(a.out_alpha[pix] > 0.f)) a.out_depth[pix] = maxd;  // neighbours ignore the stored value when alpha == 0
+  if (a.out_surface_normal) {
+    float n[3] = {0.f, 0.f, 0.f};
+    if (i > 0 && j > 0 && i < H - 1 && j < W - 1) {
+      const Intr k = load_intr(a.K);
+      stencil_normal(k, i, j, depth_at, n);
+    }
+    // flip y,z (dn_model.py:600-602) and map to [0,1] (:603); border stays exactly 0.5
+    a.out_surface_normal[pix * 3 + 0] = (1.0f + n[0]) * 0.5f;
+    a.out_surface_normal[pix * 3 + 1] = (1.0f - n[1]) * 0.5f;
+    a.out_surface_normal[pix * 3 + 2] = (1.0f - n[2]) * 0.5f;
+  }
+}
+
+__global__ void __launch_bounds__(256) normal_from_depth_kernel(const DnrArgs a) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (i >= a.height || j >= a.width) return;
+  const int W = a.width, H = a.height;
+  auto depth_at = [&](int y, int x) -> float { return a.out_depth[y * W + x]; };
+  float n[3] = {0.f, 0.f, 0.f};
+  if (i > 0 && j > 0 && i < H - 1 && j < W - 1) {
+    const Intr k = load_intr(a.K);
+    stencil_normal(k, i, j, depth_at, n);
+  }
+  const int pix = i * W + j;
+  a.out_surface_normal[pix * 3 + 0] = n[0];
+  a.out_surface_normal[pix * 3 + 1] = n[1];
+  a.out_surface_normal[pix * 3 + 2] = n[2];
+}
+
+__device__ __forceinline__ float rgb_edge(const float* rgb, int p, int q) {
+  const float g = (fabsf(rgb[p * 3 + 0] - rgb[q * 3 + 0]) + fabsf(rgb[p * 3 + 1] - rgb[q * 3 + 1])) +
+                  fabsf(rgb[p * 3 + 2] - rgb[q * 3 + 2]);
+  return expf(-(g / 3.0f));
+}
+
+__device__ __forceinline__ float sgn(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+// per-pixel depth-term pieces: value (for the type) and d(value)/d(pred)
+__device__ __forceinline__ void depth_term(int type, float d, float g, float& val, float& dval) {
+  const float e = d - g;
+  if (type == 1 || type == 2) { val = logf(1.0f + fabsf(e)); dval = sgn(e) / (1.0f + fabsf(e)); }
+  else if (type == 3) { val = fabsf(e); dval = sgn(e); }
+  else { val = e * e; dval = 2.0f * e; }
+}
+
+__global__ void __launch_bounds__(256) loss_fwd_kernel(const DnrArgs a) {
+  __shared__ float red[7][8];
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int W = a.width, H = a.height;
+  float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (i < H && j < W) {
+    const int p = i * W + j;
+    if (a.depth_loss_type != 0 && a.gt_depth[p] > a.depth_tolerance) {
+      float val, dval;
+      depth_term(a.depth_loss_type, a.out_depth[p], a.gt_depth[p], val, dval);
+      if (a.depth_loss_type == 1) {
+        if (j < W - 1) { s[0] = rgb_edge(a.gt_rgb, p, p + 1) * val; s[1] = 1.f; }
+        if (i < H - 1) { s[2] = rgb_edge(a.gt_rgb, p, p + W) * val; s[3] = 1.f; }
+      } else {
+        s[0] = val; s[1] = 1.f;
+      }
+    }
+    if (a.use_normal_loss) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float n = a.out_normal[p * 3 + c];
+        s[4] += fabsf(n - a.gt_normal[p * 3 + c]);
+        if (j < W - 1) s[5] += fabsf(n - a.out_normal[(p + 1) * 3 + c]);
+        if (i < H - 1) s[6] += fabsf(n - a.out_normal[(p + W) * 3 + c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const float w = warp_sum(s[k]);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    if (t != 0.f) atomicAdd(a.loss_partials + threadIdx.x, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) loss_bwd_kernel(const DnrArgs a, float* __restrict__ v_depth, float* __restrict__ v_normal) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int W = a.width, H = a.height;
+  if (i >= H || j >= W) return;
+  const int p = i * W + j;
+  if (v_depth) {
+    float g = 0.f;
+    if (a.depth_loss_type != 0 && a.gt_depth[p] > a.depth_tolerance) {
+      float val, dval;
+      depth_term(a.depth_loss_type, a.out_depth[p], a.gt_depth[p], val, dval);
+      const float scale = a.v_loss * (1.0f + a.depth_lambda);  // quirk B6: depth_loss += lambda * depth_loss
+      if (a.depth_loss_type == 1) {
+        float w = 0.f;
+        if (j < W - 1) w += rgb_edge(a.gt_rgb, p, p + 1) / a.loss_partials[1];
+        if (i < H - 1) w += rgb_edge(a.gt_rgb, p, p + W) / a.loss_partials[3];
+        g = scale * dval * w;
+      } else {
+        g = scale * dval / a.loss_partials[1];
+      }
+    }
+    v_depth[p] = g;
+  }
+  if (v_normal) {
+    const float inv_l1 = a.v_loss / (3.0f * (float)H * (float)W);
+    const float inv_tx = (W > 1) ? a.v_loss / (3.0f * (float)H * (float)(W - 1)) : 0.f;
+    const float inv_ty = (H > 1) ? a.v_loss / (3.0f * (float)(H - 1) * (float)W) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float g = 0.f;
+      if (a.use_normal_loss) {
+        const float n = a.out_normal[p * 3 + c];
+        g = sgn(n - a.gt_normal[p * 3 + c]) * inv_l1;
+        if (j < W - 1) g += sgn(n - a.out_normal[(p + 1) * 3 + c]) * inv_tx;
+        if (j > 0) g -= sgn(a.out_normal[(p - 1) * 3 + c] - n) * inv_tx;
+        if (i < H - 1) g += sgn(n - a.out_normal[(p + W) * 3 + c]) * inv_ty;
+        if (i > 0) g -= sgn(a.out_normal[(p - W) * 3 + c] - n) * inv_ty;
+      }
+      v_normal[p * 3 + c] = g;
+    }
+  }
+}
+
+inline dim3 img_grid(const DnrArgs* a) { return dim3((a->width + 31) / 32, (a->height + 7) / 8); }
+
+}  // namespace
+
+extern "C" int dnr_finalize_fwd(const DnrArgs* a, void* stream) {
+  if (!a) return DNR_E_NULL;
+  if (a->width <= 0 || a->height <= 0) return DNR_E_SIZE;
+  if (!a->out_depth || !a->out_alpha || !a->depth_max) return DNR_E_NULL;
+  if (a->out_surface_normal && !a->K) return DNR_E_NULL;
+  finalize_fwd_kernel<<<img_grid(a), 256, 0, (cudaStream_t)stream>>>(*a);
+  DNR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dnr_normal_from_depth(const DnrArgs* a, void* stream) {
+  if (!a) return DNR_E_NULL;
+  if (a->width <= 0 || a->height <= 0) return DNR_E_SIZE;
+  if (!a->out_depth || !a->out_surface_normal || !a->K) return DNR_E_NULL;
+  normal_from_depth_kernel<<<img_grid(a), 256, 0, (cudaStream_t)stream>>>(*a);
+  DNR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dnr_loss_fwd(const DnrArgs* a, void* stream) {
+  if (!a) return DNR_E_NULL;
+  if (a->width <= 0 || a->height <= 0) return DNR_E_SIZE;
+  if (a->depth_loss_type < 0 || a->depth_loss_type > 4) return DNR_E_OPTION;
+  if (!a->loss_partials) return DNR_E_NULL;
+  if (a->depth_loss_type != 0 && (!a->out_depth || !a->gt_depth)) return DNR_E_NULL;
+  if (a->depth_loss_type == 1 && !a->gt_rgb) return DNR_E_NULL;
+  if (a->use_normal_loss && (!a->out_normal || !a->gt_normal)) return DNR_E_NULL;
+  cudaStream_t s = (cudaStream_t)stream;
+  DNR_CUDA(cudaMemsetAsync(a->loss_partials, 0, 8 * sizeof(float), s));
+  loss_fwd_kernel<<<img_grid(a), 256, 0, s>>>(*a);
+  DNR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dnr_loss_bwd(const DnrArgs* a, float* v_depth_out, float* v_normal_out, void* stream) {
+  if (!a) return DNR_E_NULL;
+  if (a->width <= 0 || a->height <= 0) return DNR_E_SIZE;
+  if (a->depth_loss_type < 0 || a->depth_loss_type > 4) return DNR_E_OPTION;
+  if (!a->loss_partials) return DNR_E_NULL;
+  if (v_depth_out && a->depth_loss_type != 0 && (!a->out_depth || !a->gt_depth)) return DNR_E_NULL;
+  if (v_depth_out && a->depth_loss_type == 1 && !a->gt_rgb) return DNR_E_NULL;
+  if (v_normal_out && a->use_normal_loss && (!a->out_normal || !a->gt_normal)) return DNR_E_NULL;
+  loss_bwd_kernel<<<img_grid(a), 256, 0, (cudaStream_t)stream>>>(*a, v_depth_out, v_normal_out);
+  DNR_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,261 @@
+"""`dn_rasterize`: the Python operator surface of the B200 depth+normal rasterizer.
+
+One autograd.Function replaces, inside DNSplatterModel.get_outputs of the reference
+(/root/reference/dn_splatter/dn_model.py):
+    :495-516  gsplat.rendering.rasterization(..., render_mode="RGB+ED", absgrad=True)
+    :526-537  background blend / clamp / depth fill
+    :543-575  per-Gaussian normals + gsplat.rasterize_gaussians (legacy, white background)
+    :577-578  normalise / remap of the normal image
+    :589-603  normal_from_depth_image on the detached depth
+All arithmetic runs in libdnr_b200.so (hand-written sm_100a CUDA) through the C ABI of include/dnr.h;
+torch only owns the device buffers and the stream.  There is no CPU / PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import NamedTuple, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+TILE = 16
+
+
+@dataclass(frozen=True)
+class RasterSettings:
+    width: int
+    height: int
+    sh_degree: int = 3
+    near_plane: float = 0.01  # dn_model.py:507
+    far_plane: float = 1e10  # dn_model.py:508
+    eps2d: float = 0.3
+    antialiased: bool = False  # rasterize_mode == "antialiased" (dn_model.py:513)
+    render_normals: bool = True  # config.predict_normals
+    activated: bool = False  # inputs already exp()/sigmoid()-activated (gsplat's own signature)
+    background: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    surface_normal: bool = True
+
+
+class RasterOutput(NamedTuple):
+    rgb: Tensor  # [H,W,3]
+    depth: Tensor  # [H,W,1]
+    normal: Tensor  # [H,W,3] in [0,1] (zeros when render_normals is False)
+    alpha: Tensor  # [H,W,1]
+    surface_normal: Tensor  # [H,W,3] in [0,1]
+    means2d: Tensor  # [N,2]; after backward carries .grad and .absgrad (dn_model.py:517-519)
+    radii: Tensor  # [N] int32
+    depths: Tensor  # [N]
+    conics: Tensor  # [N,3]
+    tiles_per_gauss: Tensor  # [N] int32
+    normals_world: Tensor  # [N,3] (gauss_params["normals"], dn_model.py:558)
+    info: dict
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts: Tensor) -> torch.device:
+    dev = ts[0].device
+    if dev.type != "cuda":
+        raise L.DnrError("dn_rasterize needs CUDA tensors: this library has no CPU path")
+    for t in ts:
+        if t is not None and t.device != dev:
+            raise L.DnrError("all tensors must live on the same CUDA device")
+    return dev
+
+
+def _base_args(s: RasterSettings, n: int, sh_bases: int, accumulate: bool = False) -> L.DnrArgs:
+    a = L.DnrArgs()
+    a.n_gauss, a.width, a.height, a.tile_size = n, s.width, s.height, TILE
+    a.sh_degree, a.sh_bases = s.sh_degree, sh_bases
+    flags = 0
+    if s.activated:
+        flags |= L.FLAG_ACTIVATED
+    if s.antialiased:
+        flags |= L.FLAG_ANTIALIASED
+    if s.render_normals:
+        flags |= L.FLAG_NORMALS
+    if accumulate:
+        flags |= L.FLAG_ACCUMULATE
+    a.flags = flags
+    a.near_plane, a.far_plane, a.eps2d, a.radius_clip = s.near_plane, s.far_plane, s.eps2d, 0.0
+    a.background[0], a.background[1], a.background[2] = s.background
+    return a
+
+
+def _set(a: L.DnrArgs, **tensors: Optional[Tensor]) -> None:
+    for k, t in tensors.items():
+        setattr(a, k, _ptr(t))
+
+
+class _DnRasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, quats, scales, opacities, sh_dc, sh_rest, viewmat, K, c2w, settings: RasterSettings, holder: dict):
+        lib = L.load()
+        s = settings
+        dev = _require_cuda(means, quats, scales, opacities, sh_dc, sh_rest, viewmat, K)
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        means, quats, scales = means.contiguous().float(), quats.contiguous().float(), scales.contiguous().float()
+        opac = opacities.contiguous().float().view(-1)
+        sh_dc, sh_rest = sh_dc.contiguous().float(), sh_rest.contiguous().float()
+        viewmat, K = viewmat.contiguous().float().view(4, 4), K.contiguous().float().view(3, 3)
+        n = means.shape[0]
+        sh_bases = 1 + sh_rest.shape[1]
+        if n == 0:
+            raise L.DnrError("dn_rasterize: empty Gaussian set")
+        if s.render_normals:
+            if c2w is None:
+                raise L.DnrError("render_normals=True needs the camera_to_world matrix")
+            c2w = c2w.contiguous().float().view(3, 4)
+        H, W = s.height, s.width
+        tiles_x, tiles_y = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
+        n_tiles = tiles_x * tiles_y
+        rec_f = L.REC_FLOATS_N if s.render_normals else L.REC_FLOATS
+        st = _stream()
+
+        radii = torch.empty(n, **i32)
+        means2d = torch.empty(n, 2, **f32)
+        depths = torch.empty(n, **f32)
+        conics = torch.empty(n, 3, **f32)
+        opac_act = torch.empty(n, **f32)
+        comp = torch.empty(n, **f32) if s.antialiased else None
+        colors = torch.empty(n, 3, **f32)
+        normals_world = torch.empty(n, 3, **f32) if s.render_normals else torch.zeros(n, 3, **f32)
+        tiles_per_gauss = torch.empty(n, **i32)
+        depth_keys = torch.empty(n, **i32)
+        records = torch.empty(n, rec_f, **f32)
+
+        a = _base_args(s, n, sh_bases)
+        _set(a, viewmat=viewmat, K=K, c2w=c2w, means=means, quats=quats, scales=scales, opacities=opac, sh_dc=sh_dc,
+             sh_rest=sh_rest if sh_bases > 1 else None, radii=radii, means2d=means2d, depths=depths, conics=conics,
+             opac_act=opac_act, compensations=comp, colors=colors,
+             normals_world=normals_world if s.render_normals else None, tiles_per_gauss=tiles_per_gauss,
+             depth_keys=depth_keys, records=records)
+        L.check(lib.dnr_project_fwd(C.byref(a), st), "dnr_project_fwd")
+
+        ws_scan = torch.empty(lib.dnr_bin_scan_workspace_bytes(n), dtype=torch.uint8, device=dev)
+        _set(a, ws_scan=ws_scan)
+        total = C.c_int64(0)
+        L.check(lib.dnr_bin_scan(C.byref(a), st, C.byref(total)), "dnr_bin_scan")
+        n_isects = int(total.value)
+        a.n_isects = n_isects
+        ws_sort = torch.empty(lib.dnr_bin_sort_workspace_bytes(n, n_isects, n_tiles), dtype=torch.uint8, device=dev)
+        flatten_ids = torch.empty(max(n_isects, 1), **i32)
+        tile_offsets = torch.empty(n_tiles + 1, **i32)
+        _set(a, ws_sort=ws_sort, flatten_ids=flatten_ids, tile_offsets=tile_offsets)
+        L.check(lib.dnr_bin_sort(C.byref(a), st), "dnr_bin_sort")
+
+        out_rgb = torch.empty(H, W, 3, **f32)
+        out_depth = torch.empty(H, W, 1, **f32)
+        out_alpha = torch.empty(H, W, 1, **f32)
+        out_normal = torch.empty(H, W, 3, **f32) if s.render_normals else None
+        normal_norm = torch.empty(H, W, **f32) if s.render_normals else None
+        out_sn = torch.empty(H, W, 3, **f32) if s.surface_normal else None
+        last_ids = torch.empty(H, W, **i32)
+        clamp_mask = torch.empty(H, W, dtype=torch.uint8, device=dev)
+        depth_max = torch.empty(1, **i32)
+        _set(a, out_rgb=out_rgb, out_depth=out_depth, out_alpha=out_alpha, out_normal=out_normal,
+             out_surface_normal=out_sn, last_ids=last_ids, normal_norm=normal_norm, clamp_mask=clamp_mask,
+             depth_max=depth_max)
+        L.check(lib.dnr_raster_fwd(C.byref(a), st), "dnr_raster_fwd")
+        L.check(lib.dnr_finalize_fwd(C.byref(a), st), "dnr_finalize_fwd")
+
+        ctx.settings, ctx.n, ctx.sh_bases, ctx.n_isects = s, n, sh_bases, n_isects
+        ctx.save_for_backward(means, quats, scales, opac, sh_dc, sh_rest, viewmat, K, c2w if s.render_normals else None)
+        ctx.state = dict(radii=radii, records=records, flatten_ids=flatten_ids, tile_offsets=tile_offsets,
+                         out_depth=out_depth, out_alpha=out_alpha, out_normal=out_normal, last_ids=last_ids,
+                         normal_norm=normal_norm, clamp_mask=clamp_mask, means2d=means2d)
+        ctx.opac_shape = opacities.shape
+        normal_ret = out_normal if s.render_normals else torch.zeros(H, W, 3, **f32)
+        sn_ret = out_sn if s.surface_normal else torch.zeros(H, W, 3, **f32)
+        info = dict(flatten_ids=flatten_ids[:n_isects], tile_offsets=tile_offsets, last_ids=last_ids, n_isects=n_isects,
+                    colors=colors, opacities=opac_act, compensations=comp, tile_width=tiles_x, tile_height=tiles_y,
+                    depth_max=depth_max)
+        holder.update(info)
+        ctx.mark_non_differentiable(sn_ret, means2d, radii, depths, conics, tiles_per_gauss, normals_world)
+        return (out_rgb, out_depth, normal_ret, out_alpha, sn_ret, means2d, radii, depths, conics, tiles_per_gauss,
+                normals_world)
+
+    @staticmethod
+    def backward(ctx, v_rgb, v_depth, v_normal, v_alpha, *_unused):
+        lib = L.load()
+        s: RasterSettings = ctx.settings
+        means, quats, scales, opac, sh_dc, sh_rest, viewmat, K, c2w = ctx.saved_tensors
+        S = ctx.state
+        n, dev = ctx.n, means.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        st = _stream()
+
+        def prep(g):
+            return None if g is None else g.contiguous().float()
+
+        v_rgb, v_depth, v_alpha = prep(v_rgb), prep(v_depth), prep(v_alpha)
+        v_normal = prep(v_normal) if s.render_normals else None
+        grad_records = torch.empty(n, L.GRAD_FLOATS, **f32)
+        a = _base_args(s, n, ctx.sh_bases)
+        a.n_isects = ctx.n_isects
+        _set(a, viewmat=viewmat, K=K, c2w=c2w, means=means, quats=quats, scales=scales, opacities=opac, sh_dc=sh_dc,
+             sh_rest=sh_rest if ctx.sh_bases > 1 else None, radii=S["radii"], records=S["records"],
+             flatten_ids=S["flatten_ids"], tile_offsets=S["tile_offsets"], out_depth=S["out_depth"],
+             out_alpha=S["out_alpha"], out_normal=S["out_normal"], last_ids=S["last_ids"],
+             normal_norm=S["normal_norm"], clamp_mask=S["clamp_mask"], v_rgb=v_rgb, v_depth=v_depth,
+             v_normal=v_normal, v_alpha=v_alpha, grad_records=grad_records)
+        L.check(lib.dnr_raster_bwd(C.byref(a), st), "dnr_raster_bwd")
+        v_means = torch.empty_like(means)
+        v_quats = torch.empty_like(quats)
+        v_scales = torch.empty_like(scales)
+        v_opac = torch.empty_like(opac)
+        v_sh_dc = torch.empty_like(sh_dc)
+        v_sh_rest = torch.empty_like(sh_rest)
+        v_m2d = torch.empty(n, 2, **f32)
+        v_m2d_abs = torch.empty(n, 2, **f32)
+        _set(a, v_means=v_means, v_quats=v_quats, v_scales=v_scales, v_opacities=v_opac, v_sh_dc=v_sh_dc,
+             v_sh_rest=v_sh_rest if ctx.sh_bases > 1 else None, v_means2d=v_m2d, v_means2d_abs=v_m2d_abs)
+        L.check(lib.dnr_project_bwd(C.byref(a), st), "dnr_project_bwd")
+        # what nerfstudio's after_train reads: self.xys.grad / self.xys.absgrad (dn_model.py:517-519)
+        S["means2d"].grad = v_m2d
+        S["means2d"].absgrad = v_m2d_abs
+        return (v_means, v_quats, v_scales, v_opac.view(ctx.opac_shape), v_sh_dc, v_sh_rest, None, None, None, None, None)
+
+
+def dn_rasterize(
+    means: Tensor, quats: Tensor, scales: Tensor, opacities: Tensor, sh_dc: Tensor, sh_rest: Tensor,
+    viewmat: Tensor, K: Tensor, width: int, height: int, *, sh_degree: int = 3, near_plane: float = 0.01,
+    far_plane: float = 1e10, eps2d: float = 0.3, antialiased: bool = False,
+    background: Sequence[float] = (0.0, 0.0, 0.0), render_normals: bool = True, c2w: Optional[Tensor] = None,
+    activated: bool = False, surface_normal: bool = True,
+) -> RasterOutput:
+    """Renders one view.  Inputs are the reference's RAW gauss_params (log-scales, opacity logits,
+    un-normalised wxyz quats, SH coefficients split as features_dc / features_rest) unless
+    ``activated=True``.  `viewmat` is the OpenCV world->camera matrix of nerfstudio's get_viewmat,
+    `c2w` the un-optimised nerfstudio camera_to_world [3,4] (only used for normals)."""
+    if isinstance(background, Tensor):
+        background = background.detach().flatten().tolist()
+    bg = tuple(float(b) for b in background)
+    settings = RasterSettings(width=int(width), height=int(height), sh_degree=int(sh_degree), near_plane=near_plane,
+                              far_plane=far_plane, eps2d=eps2d, antialiased=antialiased, render_normals=render_normals,
+                              activated=activated, background=bg, surface_normal=surface_normal)
+    info: dict = {}
+    outs = _DnRasterize.apply(means, quats, scales, opacities, sh_dc, sh_rest, viewmat, K, c2w, settings, info)
+    return RasterOutput(*outs, info)
+
+
+def get_viewmat(c2w: Tensor) -> Tensor:
+    """nerfstudio `get_viewmat` [EXT]: OpenGL camera_to_world [..,3,4] -> OpenCV world->camera [4,4]."""
+    c2w = c2w.reshape(3, 4)
+    R = c2w[:, :3] * torch.tensor([1.0, -1.0, -1.0], dtype=c2w.dtype, device=c2w.device)
+    Rinv = R.T
+    vm = torch.zeros(4, 4, dtype=c2w.dtype, device=c2w.device)
+    vm[:3, :3] = Rinv
+    vm[:3, 3] = -(Rinv @ c2w[:, 3])
+    vm[3, 3] = 1.0
+    return vm

@@ -1,0 +1,176 @@
+/*
+ * dnr.h — C ABI of libdnr_b200.so: the B200 (sm_100a) depth+normal Gaussian rasterizer that
+ * replaces the two gsplat calls (and the torch glue between them) inside
+ * DNSplatterModel.get_outputs of maturk/dn-splatter.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/):
+ *   dnr_project_fwd    gsplat fully_fused_projection + spherical_harmonics + param activations
+ *                      (dn_splatter/dn_model.py:495-500 arguments of rasterization();
+ *                      :543-560 per-Gaussian normals)
+ *   dnr_bin_scan/sort  gsplat isect_tiles + radix sort + isect_offset_encode, shared by the colour and
+ *                      the normal pass (dn_model.py:495-516 and the second binning hidden in :564-575)
+ *   dnr_raster_fwd     gsplat rasterize_to_pixels (RGB+ED, dn_model.py:495-516) + legacy
+ *                      rasterize_gaussians on normals (:564-575) + blend/clamp/normalise (:526-537,:577-578)
+ *   dnr_finalize_fwd   depth fill with the global max (dn_model.py:534-537) + normal_from_depth_image
+ *                      (dn_splatter/utils/normal_utils.py:25-48, called at dn_model.py:589-603)
+ *   dnr_raster_bwd     autograd backward of the two rasterizations and of the glue above
+ *   dnr_project_bwd    autograd backward of projection / SH / activations / normals
+ *   dnr_loss_*         DNRegularization depth + normal terms (dn_splatter/regularization_strategy.py:146-193,
+ *                      dn_splatter/losses.py:155-224,279-295) fused: value + per-pixel gradient
+ *
+ * Conventions: plain C, POD only, every pointer is a DEVICE pointer unless named *_host, row-major
+ * contiguous fp32, images [H,W,C], quaternions wxyz, viewmat = world->camera (OpenCV), pixel centres
+ * at +0.5, tile size 16.  The caller owns every buffer (including workspaces sized by the *_bytes
+ * queries).  All work is enqueued on the stream passed in (a cudaStream_t cast to void*); the only
+ * host synchronisation is the documented n_isects read-back inside dnr_bin_scan.
+ * Return value: 0 = ok, <0 = DNR_E_* argument error, >0 = cudaError_t of a failed launch.
+ * No global state, re-entrant, never throws, never prints.
+ */
+#ifndef DNR_H_
+#define DNR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DNR_VERSION 100 /* 0.1.0 */
+
+#define DNR_E_NULL (-1)     /* a required pointer is NULL */
+#define DNR_E_SIZE (-2)     /* non-positive / inconsistent sizes */
+#define DNR_E_OPTION (-3)   /* unsupported option (tile size, sh degree, ...) */
+#define DNR_E_OVERFLOW (-4) /* more than 2^31-1 tile intersections */
+#define DNR_E_WORKSPACE (-5)/* workspace too small */
+
+/* flags */
+#define DNR_FLAG_ACTIVATED 1u   /* scales/opacities are already exp()/sigmoid()-activated (gsplat's signature) */
+#define DNR_FLAG_ANTIALIASED 2u /* rasterize_mode == "antialiased": opacity *= compensation */
+#define DNR_FLAG_NORMALS 4u     /* predict_normals: render the per-Gaussian normal channels */
+#define DNR_FLAG_ACCUMULATE 8u  /* project_bwd adds into the parameter-gradient buffers */
+
+/* floats per packed per-Gaussian raster record, without / with normals */
+#define DNR_REC_FLOATS 12
+#define DNR_REC_FLOATS_N 16
+/* floats per per-Gaussian raster-gradient record (always) */
+#define DNR_GRAD_FLOATS 16
+
+typedef struct DnrArgs {
+  /* ---- sizes and options (host scalars) ---- */
+  int32_t n_gauss;   /* N */
+  int32_t width, height;
+  int32_t tile_size; /* must be 16 (dn_model.py:470-472) */
+  int32_t sh_degree; /* active degree 0..3 (dn_model.py:487-490) */
+  int32_t sh_bases;  /* bases stored per Gaussian: sh_rest is [N, sh_bases-1, 3] */
+  uint32_t flags;    /* DNR_FLAG_* */
+  int32_t reserved0;
+  float near_plane, far_plane, eps2d, radius_clip;
+  float background[3];
+  float reserved1;
+  int64_t n_isects; /* I: filled by the caller from dnr_bin_scan's result */
+
+  /* ---- camera (device) ---- */
+  const float* viewmat; /* [4,4] */
+  const float* K;       /* [3,3] */
+  const float* c2w;     /* [3,4] nerfstudio camera_to_world (OpenGL, un-optimised); normals only */
+
+  /* ---- Gaussian parameters (device, the reference's gauss_params layout, dn_model.py:227-237) ---- */
+  const float* means;     /* [N,3] */
+  const float* quats;     /* [N,4] */
+  const float* scales;    /* [N,3] log-scales (or activated with DNR_FLAG_ACTIVATED) */
+  const float* opacities; /* [N]   logits     (or activated) */
+  const float* sh_dc;     /* [N,3] */
+  const float* sh_rest;   /* [N,sh_bases-1,3] (may be NULL when sh_bases==1) */
+
+  /* ---- projection outputs (info dict of gsplat.rasterization, dn_model.py:517-524) ---- */
+  int32_t* radii;           /* [N] */
+  float* means2d;           /* [N,2] */
+  float* depths;            /* [N] */
+  float* conics;            /* [N,3] */
+  float* opac_act;          /* [N] activated (x compensation) opacity */
+  float* compensations;     /* [N] or NULL */
+  float* colors;            /* [N,3] clamp_min(SH+0.5,0) */
+  float* normals_world;     /* [N,3] flipped world normals (gauss_params["normals"], dn_model.py:558) or NULL */
+  int32_t* tiles_per_gauss; /* [N] */
+  uint32_t* depth_keys;     /* [N] bit pattern of depth, 0xFFFFFFFF when culled */
+  float* records;           /* [N, DNR_REC_FLOATS(_N)] packed raster records */
+
+  /* ---- binning ---- */
+  void* ws_scan;         /* dnr_bin_scan_workspace_bytes(N) */
+  void* ws_sort;         /* dnr_bin_sort_workspace_bytes(N, I, n_tiles) */
+  int32_t* flatten_ids;  /* [I] Gaussian ids sorted by (tile, depth, id) */
+  int32_t* tile_offsets; /* [n_tiles+1] */
+
+  /* ---- raster forward outputs / backward state ---- */
+  float* out_rgb;      /* [H,W,3] clamp(C + (1-alpha) bg, 0, 1) */
+  float* out_depth;    /* [H,W]   D/alpha, then filled by dnr_finalize_fwd */
+  float* out_alpha;    /* [H,W] */
+  float* out_normal;   /* [H,W,3] (n/|n|+1)/2 or NULL */
+  float* out_surface_normal; /* [H,W,3] or NULL */
+  int32_t* last_ids;   /* [H,W] */
+  float* normal_norm;  /* [H,W] |n_raw| (backward state) or NULL */
+  uint8_t* clamp_mask; /* [H,W] bit k set: rgb channel k passes gradient */
+  int32_t* depth_max;  /* [1] bit pattern of max expected depth */
+
+  /* ---- raster backward ---- */
+  const float* v_rgb;    /* [H,W,3] or NULL */
+  const float* v_depth;  /* [H,W]   or NULL */
+  const float* v_normal; /* [H,W,3] or NULL */
+  const float* v_alpha;  /* [H,W]   or NULL */
+  float* grad_records;   /* [N, DNR_GRAD_FLOATS] zeroed by dnr_raster_bwd */
+
+  /* ---- projection backward outputs ---- */
+  float* v_means;       /* [N,3] */
+  float* v_quats;       /* [N,4] */
+  float* v_scales;      /* [N,3] */
+  float* v_opacities;   /* [N] */
+  float* v_sh_dc;       /* [N,3] */
+  float* v_sh_rest;     /* [N,sh_bases-1,3] */
+  float* v_means2d;     /* [N,2] or NULL  (info["means2d"].grad) */
+  float* v_means2d_abs; /* [N,2] or NULL  (info["means2d"].absgrad) */
+
+  /* ---- fused regularisers (DNRegularization) ---- */
+  const float* gt_depth;  /* [H,W] */
+  const float* gt_normal; /* [H,W,3] */
+  const float* gt_rgb;    /* [H,W,3] */
+  float* loss_partials;   /* [8] fp32 accumulators, see dnr_loss_fwd */
+  float depth_lambda, depth_tolerance;
+  int32_t depth_loss_type; /* 0 none, 1 EdgeAwareLogL1, 2 LogL1, 3 L1, 4 MSE */
+  int32_t use_normal_loss;
+  float v_loss;            /* upstream gradient of the scalar regulariser */
+  float reserved2;
+} DnrArgs;
+
+int dnr_version(void);
+const char* dnr_error_string(int code);
+
+int dnr_project_fwd(const DnrArgs* a, void* stream);
+
+size_t dnr_bin_scan_workspace_bytes(int32_t n_gauss);
+/* Sorts visible Gaussians by depth, scans their tile counts, copies the total to *n_isects_host and
+ * synchronises the stream (the one documented host sync). */
+int dnr_bin_scan(const DnrArgs* a, void* stream, int64_t* n_isects_host);
+size_t dnr_bin_sort_workspace_bytes(int32_t n_gauss, int64_t n_isects, int32_t n_tiles);
+int dnr_bin_sort(const DnrArgs* a, void* stream);
+
+int dnr_raster_fwd(const DnrArgs* a, void* stream);
+int dnr_finalize_fwd(const DnrArgs* a, void* stream);
+/* normal_from_depth_image for an arbitrary depth map: depth in a->out_depth, result (un-flipped,
+ * un-remapped, zero border) in a->out_surface_normal; intrinsics from a->K. */
+int dnr_normal_from_depth(const DnrArgs* a, void* stream);
+
+int dnr_raster_bwd(const DnrArgs* a, void* stream);
+int dnr_project_bwd(const DnrArgs* a, void* stream);
+
+/* DNRegularization depth + normal terms on the rendered maps.  loss_partials (zeroed by the call):
+ * [0] sum_x  [1] count_x  [2] sum_y  [3] count_y  (depth term; for non edge-aware types only x is used)
+ * [4] sum |n - n_gt|   [5] sum |dW n|   [6] sum |dH n|.   dnr_loss_bwd writes d(loss)/d(depth),
+ * d(loss)/d(normal) into a->v_depth / a->v_normal style buffers passed as out pointers. */
+int dnr_loss_fwd(const DnrArgs* a, void* stream);
+int dnr_loss_bwd(const DnrArgs* a, float* v_depth_out, float* v_normal_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DNR_H_ */

@@ -18,14 +18,17 @@ def oracle_outputs(params, cam, dtype=torch.float32, requires_grad=False, **kw):
     return p, out
 
 
-def cuda_outputs(params, cam, requires_grad=False, device="cuda", **kw):
+def cuda_outputs(params, cam, requires_grad=False, device="cuda", viewmat=None, **kw):
+    """`viewmat`: pass the oracle's own matrix when bit-exactness of integer outputs is asserted (a GPU matmul
+    rounds the translation column differently from the CPU one)."""
     from dn_splatter_b200 import dn_rasterize, get_viewmat
 
     p = {k: v.detach().clone().to(device).requires_grad_(requires_grad) for k, v in params.items()}
     c2w = cam["c2w"].to(device)
     K = torch.tensor([[cam["fx"], 0, cam["cx"]], [0, cam["fy"], cam["cy"]], [0, 0, 1]], dtype=torch.float32, device=device)
     out = dn_rasterize(p["means"], p["quats"], p["scales"], p["opacities"], p["features_dc"], p["features_rest"],
-                       get_viewmat(c2w), K, cam["width"], cam["height"], background=BACKGROUND, c2w=c2w, **kw)
+                       get_viewmat(c2w) if viewmat is None else viewmat.to(device), K, cam["width"], cam["height"],
+                       background=BACKGROUND, c2w=c2w, **kw)
     return p, out
 
 

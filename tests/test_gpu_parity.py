@@ -45,7 +45,7 @@ def test_projection_and_binning_bit_exact(case):
     proj = G.project_gaussians(act["means"], act["quats"], act["scales"], vm, K, W, H)
     tpg, isect_ids, flat, offs, _ = G.isect_tiles(proj["means2d"], proj["radii"], proj["depths"], 16, W, H)
 
-    _, out = cuda_outputs(act, cam, activated=True)
+    _, out = cuda_outputs(act, cam, activated=True, viewmat=vm)
     assert torch.equal(out.radii.cpu(), proj["radii"]), "radii must be bit-exact"
     assert torch.equal(out.tiles_per_gauss.cpu(), tpg), "tiles_per_gauss must be bit-exact"
     for name, got, want in (("means2d", out.means2d, proj["means2d"]), ("depths", out.depths, proj["depths"]),

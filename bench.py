@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — rendered Mpix/s (forward+backward, RGB + depth + normal) of the dn-splatter hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference ...                           # the reference's CPU path (oracle port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU, per-camera sharding
+
+A step = one pass of the hot path over one batch: every rank renders ONE 1080p view of the 1M-Gaussian
+synthetic scene through the public API (DNSplatterModel.get_outputs -> get_loss_dict -> backward):
+project -> bin/sort -> composite RGB+depth+normal -> depth fill + surface normal -> DNRegularization
+(EdgeAwareLogL1 depth, L1+TV normal, min-scale) + L1 photometric -> raster backward -> projection backward
+(straight into the flat gradient bucket) -> [N>1: one NCCL all-reduce of the bucket].
+`value` is measured with the supervision maps resident in HBM; `e2e` pulls each step's maps from pinned host
+memory (H2D inside the timed region) and reads the loss back (D2H).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "rendered Mpix/s (fwd+bwd, RGB+depth+normal)"
+HANDWRITTEN_LAUNCHES_PER_STEP = 13  # project_fwd iota emit offsets raster_fwd finalize loss_fwd loss_finish
+#                                     scale_loss_fwd | scale_loss_bwd loss_bwd raster_bwd project_bwd
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-gauss", type=int, default=1_000_000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--views", type=int, default=200)
+    ap.add_argument("--gt-sets", type=int, default=16, help="distinct supervision-map sets cycled over the views")
+    ap.add_argument("--no-normals", action="store_true", help="BASELINE config C2 literal: RGB+depth only")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--cpu-crop", default="384x216")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def build_workload(args, device, normals: bool):
+    from dn_splatter_b200.cameras import Cameras
+    from dn_splatter_b200.dn_model import DNSplatterModelConfig
+    from dn_splatter_b200.losses import DepthLossType
+    from dn_splatter_b200.synthetic import make_scene, ring_cameras
+
+    cfg = DNSplatterModelConfig(
+        random_init=True, num_random=16, use_depth_loss=True, depth_lambda=0.2, depth_loss_type=DepthLossType.EdgeAwareLogL1,
+        predict_normals=normals, use_normal_loss=normals, normal_supervision="mono", ssim_lambda=0.0, background_color="black",
+    )
+    model = cfg.setup(device=device)
+    model.load_gaussians(make_scene(args.n_gauss, seed=0))
+    model.background_color = torch.tensor([0.1490, 0.1647, 0.2157])
+    model.step = 30000  # full SH degree (sh_degree_interval schedule done)
+    model.train()
+    bucket = model.enable_flat_grads()
+    cams = [Cameras(c["c2w"][None].to(device), c["fx"], c["fy"], c["cx"], c["cy"], c["width"], c["height"],
+                    metadata={"cam_idx": i}) for i, c in enumerate(ring_cameras(args.views, args.width, args.height))]
+    return model, bucket, cams
+
+
+def make_gt_sets(model, cams, args, normals: bool, n_sets: int):
+    """Synthetic supervision: gt rgb = U[0,1) as uint8, gt depth = the scene's own depth rendered
+    from a perturbed copy (dense, > 0.1), gt normal = normal_from_depth_image(gt depth) in [0,1]."""
+    from dn_splatter_b200.utils.normal_utils import normal_from_depth_image
+
+    g = torch.Generator().manual_seed(1)
+    H, W = args.height, args.width
+    sets = []
+    saved = model.gauss_params["means"].data
+    model.gauss_params["means"].data = saved + 0.01 * torch.randn(saved.shape, generator=g).to(saved.device)
+    with torch.no_grad():
+        for s in range(n_sets):
+            cam = cams[(s * max(1, len(cams) // n_sets)) % len(cams)]
+            out = model.get_outputs(cam)
+            depth = out["depth"].clone()
+            depth = torch.where(depth > 0.1, depth, torch.full_like(depth, 5.0))
+            batch = {"image": (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8), "mono_depth": depth.cpu()}
+            if normals:
+                n = normal_from_depth_image(depth, float(cam.fx[0, 0]), float(cam.fy[0, 0]), float(cam.cx[0, 0]),
+                                            float(cam.cy[0, 0]), (W, H), torch.eye(4, device=depth.device), depth.device)
+                batch["normal"] = ((1 + n * torch.tensor([1.0, -1.0, -1.0], device=n.device)) / 2).cpu()
+            sets.append(batch)
+    model.gauss_params["means"].data = saved
+    return sets
+
+
+def run_step(model, bucket, cam, batch):
+    bucket.zero_()
+    outputs = model.get_outputs(cam)
+    loss_dict = model.get_loss_dict(outputs, dict(batch))
+    loss = loss_dict["main_loss"] + loss_dict["scale_reg"]
+    loss.backward()
+    bucket.all_reduce()
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_sample(args, normals: bool, crop: str):
+    """The reference's pure-PyTorch CPU path (oracle/: gsplat-1.0.0 restatement + dn-splatter glue + the
+    reference's regularisers), forward+backward, on a centred crop of view 0 of the SAME scene."""
+    from dn_splatter_b200.synthetic import BACKGROUND, make_scene, ring_cameras
+    from oracle import dn_ref
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cw, ch = (int(x) for x in crop.split("x"))
+    cw, ch = min(cw, args.width), min(ch, args.height)
+    params = {k: v.requires_grad_(True) for k, v in make_scene(args.n_gauss, seed=0).items()}
+    cam = ring_cameras(args.views, args.width, args.height)[0]
+    cx, cy = cam["cx"] - (args.width - cw) / 2, cam["cy"] - (args.height - ch) / 2
+    g = torch.Generator().manual_seed(1)
+    gt_img = torch.rand(ch, cw, 3, generator=g).clamp(min=10 / 255.0)
+    t0 = time.perf_counter()
+    out = dn_ref.get_outputs(params, cam["c2w"], cam["fx"], cam["fy"], cx, cy, cw, ch, torch.tensor(BACKGROUND),
+                             predict_normals=normals)
+    gt_depth = (out["depth"].detach() + 0.05).clamp(min=0.2)
+    gt_normal = out["surface_normal"].detach()
+    reg = dn_ref.dn_regularization(out["depth"], gt_depth, out["normal"], gt_normal, params["scales"], gt_img,
+                                   depth_lambda=0.2, use_normal_loss=normals)
+    loss = (out["rgb"] - gt_img).abs().mean() + reg
+    loss.backward()
+    dt = time.perf_counter() - t0
+    return {"value": cw * ch / 1e6 / dt, "unit": "Mpix/s", "cores": cores, "kind": "port",
+            "sample": f"1 view, centred {cw}x{ch} crop of the {args.width}x{args.height} frame, N={args.n_gauss}, fwd+bwd, "
+                      f"{dt:.1f} s; oracle/ = CPU port of gsplat-1.0.0 + the reference's own loss code (gsplat is CUDA-only "
+                      f"and absent)"}, dt
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    normals = not args.no_normals
+    steps, warm = max(1, min(args.steps, 3)), 0
+    vals, last = [], None
+    for _ in range(steps):
+        last, dt = cpu_reference_sample(args, normals, args.cpu_crop)
+        vals.append(last["value"])
+    v = sum(vals) / len(vals)
+    last["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * (int(args.cpu_crop.split("x")[0]) * int(args.cpu_crop.split("x")[1]) / 1e6) / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, normals, 1), "cpu_baseline": last,
+        "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, normals, world):
+    return {
+        "workload": f"BASELINE configs[1]: {args.n_gauss} Gaussians, {args.views} synthetic ring views {args.width}x{args.height}, "
+                    f"{'RGB+depth+normal' if normals else 'RGB+depth'} render fwd+bwd, 1 view per GPU per step",
+        "n_gauss": args.n_gauss, "width": args.width, "height": args.height, "views": args.views, "sh_degree": 3,
+        "normals": normals, "losses": "L1 rgb + DNRegularization(EdgeAwareLogL1 depth (1+0.2), L1+TV normal, min-scale); "
+                                      "SSIM and the optimizer step are SURVEY §8f 'next' rows, not in the step",
+        "parallelism": f"per-camera sharding x{world}, one flat all-reduce/step" if world > 1 else "single GPU",
+        "l2_policy": "inputs larger than L2 (236 MB parameters + 26M-intersection lists per view)", "gt_sets": args.gt_sets,
+    }
+
+
+# ------------------------------------------------------------------------------------------------ main (ours)
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    normals = not args.no_normals
+    import dn_splatter_b200.rasterize as R
+
+    model, bucket, cams = build_workload(args, device, normals)
+    my_views = list(range(rank, len(cams), world)) or [0]
+    host_sets = make_gt_sets(model, cams, args, normals, args.gt_sets)
+    dev_sets = [{k: v.to(device) for k, v in b.items()} for b in host_sets]
+    pin_sets = [{k: v.pin_memory() for k, v in b.items()} for b in host_sets]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, step_fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(n_steps):
+            step_fn(s)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def resident_step(s):
+        run_step(model, bucket, cams[my_views[s % len(my_views)]], dev_sets[s % len(dev_sets)])
+
+    losses = []
+
+    def e2e_step(s):
+        b = {k: v.to(device, non_blocking=True) for k, v in pin_sets[s % len(pin_sets)].items()}
+        loss = run_step(model, bucket, cams[my_views[s % len(my_views)]], b)
+        losses.append(float(loss.item()))  # D2H read of the step's result
+
+    # warm-up, then the timed device-resident run
+    for s in range(max(3, args.warmup)):
+        resident_step(s)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(args.steps, resident_step)
+    clocks = sampler.stop() if rank == 0 else None
+    pix = args.width * args.height
+    value = world * args.steps * pix / 1e6 / (ms / 1e3)
+
+    e2e = None
+    if not args.skip_e2e:
+        for s in range(3):
+            e2e_step(s)
+        ms_e = timed(args.steps, e2e_step)
+        e2e = {"value": world * args.steps * pix / 1e6 / (ms_e / 1e3), "unit": "Mpix/s", "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": 4, "ms_per_step": ms_e / args.steps}
+
+    # per-stage device times (CUDA events on the launching stream) for the roofline of the dominant kernel
+    stages, roof = {}, None
+    if rank == 0:
+        R.STAGE_EVENTS = []
+        n_prof = min(args.steps, 10)
+        for s in range(n_prof):
+            resident_step(s)
+        torch.cuda.synchronize()
+        for name, a, b in R.STAGE_EVENTS:
+            stages[name] = stages.get(name, 0.0) + a.elapsed_time(b) / n_prof
+        R.STAGE_EVENTS = None
+        out = model.raster_out
+        info = out.info
+        I = int(info["n_isects"])
+        to = info["tile_offsets"].long()
+        tiles_x = info["tile_width"]
+        H, W = args.height, args.width
+        last = info["last_ids"].long()
+        # intersections actually composited: per tile, up to the deepest last_id of its pixels
+        pad_h, pad_w = (-H) % 16, (-W) % 16
+        lp = torch.nn.functional.pad(last, (0, pad_w, 0, pad_h), value=-1)
+        tmax = lp.view((H + pad_h) // 16, 16, (W + pad_w) // 16, 16).amax(dim=(1, 3)).reshape(-1)
+        i_eff = int(torch.clamp(torch.minimum(tmax + 1, to[1:]) - to[:-1], min=0).sum())
+        cn = 1 if normals else 0
+        P = H * W
+        from json import load as _jl
+
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(_jl(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        G = 48 + 12 * cn
+        alg = {
+            "raster_bwd": (28 + 12 * cn) * P + (20 + 12 * cn) * P + (4 + 44 + 12 * cn) * i_eff + G * i_eff,
+            "raster_fwd": (4 + 44 + 12 * cn) * i_eff + (28 + 12 * cn) * P,
+            "bin_sort": 44 * I,
+            "project_fwd": (44 + 32 + 12 * 16 + 12 + 12 * cn) * args.n_gauss,
+            "project_bwd": (G + 44 + 44 + 12 * 16) * args.n_gauss,
+        }
+        dom = max((k for k in stages if k in alg), key=lambda k: stages[k])
+        ach = alg[dom] / (stages[dom] / 1e3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
+                "n_isects": I, "n_isects_composited": i_eff, "ms_per_launch": stages[dom]}
+
+    cpu = None
+    if rank == 0 and not args.skip_cpu_baseline and world == 1:
+        cpu, _ = cpu_reference_sample(args, normals, args.cpu_crop)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, normals, world), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": HANDWRITTEN_LAUNCHES_PER_STEP * args.steps,
+            "gpu_launches_note": "hand-written dnr kernels only; each step also runs ~14 cub radix-sort/scan passes compiled into "
+                                 "libdnr_b200.so and ~12 torch element-wise kernels of the L1 photometric loss",
+            "roofline": roof, "stages_ms": stages, "cpu_baseline": cpu, "last_loss": losses[-1] if losses else None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -35,9 +35,8 @@ class DnrArgs(C.Structure):
         ("v_rgb", _p), ("v_depth", _p), ("v_normal", _p), ("v_alpha", _p), ("grad_records", _p),
         ("v_means", _p), ("v_quats", _p), ("v_scales", _p), ("v_opacities", _p), ("v_sh_dc", _p), ("v_sh_rest", _p),
         ("v_means2d", _p), ("v_means2d_abs", _p),
-        ("gt_depth", _p), ("gt_normal", _p), ("gt_rgb", _p), ("loss_partials", _p),
+        ("gt_depth", _p), ("gt_normal", _p), ("gt_rgb", _p), ("loss_partials", _p), ("v_loss", _p),
         ("depth_lambda", _f), ("depth_tolerance", _f), ("depth_loss_type", _i), ("use_normal_loss", _i),
-        ("v_loss", _f), ("reserved2", _f),
     ]
 
 
@@ -74,6 +73,10 @@ def load() -> C.CDLL:
     lib.dnr_bin_scan.argtypes = [A, C.c_void_p, C.POINTER(C.c_int64)]
     lib.dnr_loss_bwd.restype = C.c_int
     lib.dnr_loss_bwd.argtypes = [A, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dnr_scale_loss_fwd.restype = C.c_int
+    lib.dnr_scale_loss_fwd.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.dnr_scale_loss_bwd.restype = C.c_int
+    lib.dnr_scale_loss_bwd.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dnr_bin_scan_workspace_bytes.restype = C.c_size_t
     lib.dnr_bin_scan_workspace_bytes.argtypes = [C.c_int32]
     lib.dnr_bin_sort_workspace_bytes.restype = C.c_size_t
@@ -85,7 +88,7 @@ def load() -> C.CDLL:
 EXPORTS = (
     "dnr_version", "dnr_error_string", "dnr_project_fwd", "dnr_bin_scan_workspace_bytes", "dnr_bin_scan",
     "dnr_bin_sort_workspace_bytes", "dnr_bin_sort", "dnr_raster_fwd", "dnr_finalize_fwd", "dnr_normal_from_depth",
-    "dnr_raster_bwd", "dnr_project_bwd", "dnr_loss_fwd", "dnr_loss_bwd",
+    "dnr_raster_bwd", "dnr_project_bwd", "dnr_loss_fwd", "dnr_loss_bwd", "dnr_scale_loss_fwd", "dnr_scale_loss_bwd",
 )
 
 

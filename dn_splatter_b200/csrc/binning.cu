@@ -13,6 +13,8 @@
 //      tile the depth order of step 1 survives, so the list equals gsplat's sort by (tile, depth, id);
 //   5. tile offsets from the sorted tile ids.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "common.cuh"
 
@@ -56,8 +58,7 @@ ScanWs carve_scan(void* base, int32_t n) {
   cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
                                   (int32_t*)nullptr, n, 0, 32);
   GatherCounts f{nullptr, nullptr, n};
-  cub::TransformInputIterator<int64_t, GatherCounts, cub::CountingInputIterator<int32_t>> it(
-      cub::CountingInputIterator<int32_t>(0), f);
+  auto it = thrust::make_transform_iterator(thrust::make_counting_iterator<int32_t>(0), f);
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, it, (int64_t*)nullptr, n + 1);
   w.cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
   w.cub_temp = (void*)(p + off); off += align_up(w.cub_bytes);
@@ -183,8 +184,7 @@ extern "C" int dnr_bin_scan(const DnrArgs* a, void* stream, int64_t* n_isects_ho
   DNR_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, bytes, (const uint32_t*)a->depth_keys, w.keys_sorted,
                                            (const int32_t*)w.iota, w.order, n, 0, 32, s));
   GatherCounts f{a->tiles_per_gauss, w.order, n};
-  cub::TransformInputIterator<int64_t, GatherCounts, cub::CountingInputIterator<int32_t>> it(
-      cub::CountingInputIterator<int32_t>(0), f);
+  auto it = thrust::make_transform_iterator(thrust::make_counting_iterator<int32_t>(0), f);
   bytes = w.cub_bytes;
   DNR_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, bytes, it, w.isect_start, n + 1, s));
   int64_t total = 0;

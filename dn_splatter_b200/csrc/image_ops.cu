@@ -148,12 +148,13 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const DnrArgs a, float* _
   const int W = a.width, H = a.height;
   if (i >= H || j >= W) return;
   const int p = i * W + j;
+  const float vl = a.v_loss ? __ldg(a.v_loss) : 1.0f;
   if (v_depth) {
     float g = 0.f;
     if (a.depth_loss_type != 0 && a.gt_depth[p] > a.depth_tolerance) {
       float val, dval;
       depth_term(a.depth_loss_type, a.out_depth[p], a.gt_depth[p], val, dval);
-      const float scale = a.v_loss * (1.0f + a.depth_lambda);  // quirk B6: depth_loss += lambda * depth_loss
+      const float scale = vl * (1.0f + a.depth_lambda);  // quirk B6: depth_loss += lambda * depth_loss
       if (a.depth_loss_type == 1) {
         float w = 0.f;
         if (j < W - 1) w += rgb_edge(a.gt_rgb, p, p + 1) / a.loss_partials[1];
@@ -166,9 +167,9 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const DnrArgs a, float* _
     v_depth[p] = g;
   }
   if (v_normal) {
-    const float inv_l1 = a.v_loss / (3.0f * (float)H * (float)W);
-    const float inv_tx = (W > 1) ? a.v_loss / (3.0f * (float)H * (float)(W - 1)) : 0.f;
-    const float inv_ty = (H > 1) ? a.v_loss / (3.0f * (float)(H - 1) * (float)W) : 0.f;
+    const float inv_l1 = vl / (3.0f * (float)H * (float)W);
+    const float inv_tx = (W > 1) ? vl / (3.0f * (float)H * (float)(W - 1)) : 0.f;
+    const float inv_ty = (H > 1) ? vl / (3.0f * (float)(H - 1) * (float)W) : 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float g = 0.f;
@@ -183,6 +184,53 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const DnrArgs a, float* _
       v_normal[p * 3 + c] = g;
     }
   }
+}
+
+__global__ void loss_finish_kernel(const DnrArgs a) {
+  float* p = a.loss_partials;
+  const int W = a.width, H = a.height;
+  float depth = 0.f;
+  if (a.depth_loss_type == 1) depth = p[0] / p[1] + p[2] / p[3];  // 0/0 = nan when nothing is valid, as torch's mean of empty
+  else if (a.depth_loss_type != 0) depth = p[0] / p[1];
+  depth = depth + a.depth_lambda * depth;  // quirk B6
+  float l1 = 0.f, tv = 0.f;
+  if (a.use_normal_loss) {
+    l1 = p[4] / (3.0f * (float)H * (float)W);
+    tv = p[5] / (3.0f * (float)H * (float)(W - 1)) + p[6] / (3.0f * (float)(H - 1) * (float)W);
+  }
+  p[8] = depth; p[9] = l1; p[10] = tv; p[11] = depth + (l1 + tv);
+}
+
+__global__ void __launch_bounds__(256) scale_loss_fwd_kernel(const float* __restrict__ scales, int n, float* out) {
+  __shared__ float red[8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float v = 0.f;
+  if (i < n) v = expf(fminf(fminf(scales[i * 3], scales[i * 3 + 1]), scales[i * 3 + 2]));
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out, t / (float)n);
+  }
+}
+
+__global__ void __launch_bounds__(256) scale_loss_bwd_kernel(const float* __restrict__ scales, int n, const float* v_loss,
+                                                            float* __restrict__ v_scales) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float vl = v_loss ? __ldg(v_loss) : 1.0f;
+  const float s0 = scales[i * 3], s1 = scales[i * 3 + 1], s2 = scales[i * 3 + 2];
+  int idx = 0;
+  float m = s0;
+  if (s1 < m) { m = s1; idx = 1; }
+  if (s2 < m) { m = s2; idx = 2; }
+  const float g = vl * expf(m) / (float)n;
+  v_scales[i * 3 + 0] = idx == 0 ? g : 0.f;
+  v_scales[i * 3 + 1] = idx == 1 ? g : 0.f;
+  v_scales[i * 3 + 2] = idx == 2 ? g : 0.f;
 }
 
 inline dim3 img_grid(const DnrArgs* a) { return dim3((a->width + 31) / 32, (a->height + 7) / 8); }
@@ -217,8 +265,10 @@ extern "C" int dnr_loss_fwd(const DnrArgs* a, void* stream) {
   if (a->depth_loss_type == 1 && !a->gt_rgb) return DNR_E_NULL;
   if (a->use_normal_loss && (!a->out_normal || !a->gt_normal)) return DNR_E_NULL;
   cudaStream_t s = (cudaStream_t)stream;
-  DNR_CUDA(cudaMemsetAsync(a->loss_partials, 0, 8 * sizeof(float), s));
+  DNR_CUDA(cudaMemsetAsync(a->loss_partials, 0, 12 * sizeof(float), s));
   loss_fwd_kernel<<<img_grid(a), 256, 0, s>>>(*a);
+  DNR_CHECK_LAUNCH();
+  loss_finish_kernel<<<1, 1, 0, s>>>(*a);
   DNR_CHECK_LAUNCH();
   return 0;
 }
@@ -232,6 +282,24 @@ extern "C" int dnr_loss_bwd(const DnrArgs* a, float* v_depth_out, float* v_norma
   if (v_depth_out && a->depth_loss_type == 1 && !a->gt_rgb) return DNR_E_NULL;
   if (v_normal_out && a->use_normal_loss && (!a->out_normal || !a->gt_normal)) return DNR_E_NULL;
   loss_bwd_kernel<<<img_grid(a), 256, 0, (cudaStream_t)stream>>>(*a, v_depth_out, v_normal_out);
+  DNR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dnr_scale_loss_fwd(const float* scales, int32_t n_gauss, float* loss_out, void* stream) {
+  if (!scales || !loss_out) return DNR_E_NULL;
+  if (n_gauss <= 0) return DNR_E_SIZE;
+  cudaStream_t s = (cudaStream_t)stream;
+  DNR_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), s));
+  scale_loss_fwd_kernel<<<(n_gauss + 255) / 256, 256, 0, s>>>(scales, n_gauss, loss_out);
+  DNR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dnr_scale_loss_bwd(const float* scales, int32_t n_gauss, const float* v_loss, float* v_scales, void* stream) {
+  if (!scales || !v_scales) return DNR_E_NULL;
+  if (n_gauss <= 0) return DNR_E_SIZE;
+  scale_loss_bwd_kernel<<<(n_gauss + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scales, n_gauss, v_loss, v_scales);
   DNR_CHECK_LAUNCH();
   return 0;
 }

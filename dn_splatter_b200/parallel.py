@@ -1,0 +1,69 @@
+"""Per-camera data parallelism: Gaussian parameters are replicated, the views of a step are
+sharded round-robin over the ranks (one process per GPU), every rank accumulates its views' per-Gaussian
+gradients into ONE flat fp32 bucket that aliases the parameters' .grad tensors, and a single NCCL all-reduce
+(sum) over NVLink/NVSwitch makes the gradients identical on all ranks.
+
+The reference only wraps the model in DDP(find_unused_parameters=True) (dn_pipeline.py:123-128), which cannot
+cope with densification re-creating parameters; this module is the working equivalent for the hot path."""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+GRAD_PARAMS = ("means", "scales", "quats", "features_dc", "features_rest", "opacities")
+
+
+class FlatGradBucket:
+    """One contiguous fp32 buffer holding the gradients of the six optimised gauss_params (59 floats per
+    Gaussian at SH degree 3); `param.grad` are views into it, so autograd, the rasterizer's grad-sink path
+    and the all-reduce all touch the same memory."""
+
+    def __init__(self, params: Dict[str, torch.nn.Parameter], names: Iterable[str] = GRAD_PARAMS):
+        self.names = [n for n in names if n in params]
+        self.params = {n: params[n] for n in self.names}
+        total = sum(p.numel() for p in self.params.values())
+        dev = next(iter(self.params.values())).device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.views: Dict[str, Tensor] = {}
+        off = 0
+        for n, p in self.params.items():
+            v = self.flat[off:off + p.numel()].view_as(p)
+            p.grad = v
+            self.views[n] = v
+            off += p.numel()
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+        for n, p in self.params.items():  # re-attach in case an optimizer set .grad = None
+            if p.grad is None or p.grad.data_ptr() != self.views[n].data_ptr():
+                p.grad = self.views[n]
+
+    def sink(self) -> Dict[str, Tensor]:
+        """Buffers for dn_rasterize(grad_sink=...)."""
+        return self.views
+
+    def all_reduce(self, group=None, async_op: bool = False):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return None
+
+
+def shard_views(n_views: int, rank: int, world_size: int) -> List[int]:
+    """Round-robin view assignment: rank r renders {i : i mod world_size == r}."""
+    return list(range(rank, n_views, world_size))
+
+
+def all_reduce_densification_stats(xys_grad_norm: Optional[Tensor], vis_counts: Optional[Tensor],
+                                   max_2Dsize: Optional[Tensor], group=None) -> None:
+    """The extra small collectives needed only at refine_every boundaries: sums and a max."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return
+    if xys_grad_norm is not None:
+        dist.all_reduce(xys_grad_norm, op=dist.ReduceOp.SUM, group=group)
+    if vis_counts is not None:
+        dist.all_reduce(vis_counts, op=dist.ReduceOp.SUM, group=group)
+    if max_2Dsize is not None:
+        dist.all_reduce(max_2Dsize, op=dist.ReduceOp.MAX, group=group)

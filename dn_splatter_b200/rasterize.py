@@ -23,6 +23,21 @@ from . import _lib as L
 
 TILE = 16
 
+# Optional per-stage device timing (bench.py's roofline pass): when STAGE_EVENTS is a list, every C-ABI
+# stage call is bracketed by CUDA events on the launching stream and (name, start, end) is appended.
+STAGE_EVENTS = None
+
+
+def _timed(name, fn, *args):
+    if STAGE_EVENTS is None:
+        return fn(*args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    STAGE_EVENTS.append((name, e0, e1))
+    return rc
+
 
 @dataclass(frozen=True)
 class RasterSettings:
@@ -140,19 +155,19 @@ class _DnRasterize(torch.autograd.Function):
              opac_act=opac_act, compensations=comp, colors=colors,
              normals_world=normals_world if s.render_normals else None, tiles_per_gauss=tiles_per_gauss,
              depth_keys=depth_keys, records=records)
-        L.check(lib.dnr_project_fwd(C.byref(a), st), "dnr_project_fwd")
+        L.check(_timed("project_fwd", lib.dnr_project_fwd, C.byref(a), st), "dnr_project_fwd")
 
         ws_scan = torch.empty(lib.dnr_bin_scan_workspace_bytes(n), dtype=torch.uint8, device=dev)
         _set(a, ws_scan=ws_scan)
         total = C.c_int64(0)
-        L.check(lib.dnr_bin_scan(C.byref(a), st, C.byref(total)), "dnr_bin_scan")
+        L.check(_timed("bin_scan", lib.dnr_bin_scan, C.byref(a), st, C.byref(total)), "dnr_bin_scan")
         n_isects = int(total.value)
         a.n_isects = n_isects
         ws_sort = torch.empty(lib.dnr_bin_sort_workspace_bytes(n, n_isects, n_tiles), dtype=torch.uint8, device=dev)
         flatten_ids = torch.empty(max(n_isects, 1), **i32)
         tile_offsets = torch.empty(n_tiles + 1, **i32)
         _set(a, ws_sort=ws_sort, flatten_ids=flatten_ids, tile_offsets=tile_offsets)
-        L.check(lib.dnr_bin_sort(C.byref(a), st), "dnr_bin_sort")
+        L.check(_timed("bin_sort", lib.dnr_bin_sort, C.byref(a), st), "dnr_bin_sort")
 
         out_rgb = torch.empty(H, W, 3, **f32)
         out_depth = torch.empty(H, W, 1, **f32)
@@ -166,8 +181,8 @@ class _DnRasterize(torch.autograd.Function):
         _set(a, out_rgb=out_rgb, out_depth=out_depth, out_alpha=out_alpha, out_normal=out_normal,
              out_surface_normal=out_sn, last_ids=last_ids, normal_norm=normal_norm, clamp_mask=clamp_mask,
              depth_max=depth_max)
-        L.check(lib.dnr_raster_fwd(C.byref(a), st), "dnr_raster_fwd")
-        L.check(lib.dnr_finalize_fwd(C.byref(a), st), "dnr_finalize_fwd")
+        L.check(_timed("raster_fwd", lib.dnr_raster_fwd, C.byref(a), st), "dnr_raster_fwd")
+        L.check(_timed("finalize_fwd", lib.dnr_finalize_fwd, C.byref(a), st), "dnr_finalize_fwd")
 
         ctx.settings, ctx.n, ctx.sh_bases, ctx.n_isects = s, n, sh_bases, n_isects
         ctx.save_for_backward(means, quats, scales, opac, sh_dc, sh_rest, viewmat, K, c2w if s.render_normals else None)
@@ -180,6 +195,7 @@ class _DnRasterize(torch.autograd.Function):
         info = dict(flatten_ids=flatten_ids[:n_isects], tile_offsets=tile_offsets, last_ids=last_ids, n_isects=n_isects,
                     colors=colors, opacities=opac_act, compensations=comp, tile_width=tiles_x, tile_height=tiles_y,
                     depth_max=depth_max)
+        ctx.grad_sink = holder.pop("grad_sink", None)
         holder.update(info)
         ctx.mark_non_differentiable(sn_ret, means2d, radii, depths, conics, tiles_per_gauss, normals_world)
         return (out_rgb, out_depth, normal_ret, out_alpha, sn_ret, means2d, radii, depths, conics, tiles_per_gauss,
@@ -209,21 +225,30 @@ class _DnRasterize(torch.autograd.Function):
              out_alpha=S["out_alpha"], out_normal=S["out_normal"], last_ids=S["last_ids"],
              normal_norm=S["normal_norm"], clamp_mask=S["clamp_mask"], v_rgb=v_rgb, v_depth=v_depth,
              v_normal=v_normal, v_alpha=v_alpha, grad_records=grad_records)
-        L.check(lib.dnr_raster_bwd(C.byref(a), st), "dnr_raster_bwd")
-        v_means = torch.empty_like(means)
-        v_quats = torch.empty_like(quats)
-        v_scales = torch.empty_like(scales)
-        v_opac = torch.empty_like(opac)
-        v_sh_dc = torch.empty_like(sh_dc)
-        v_sh_rest = torch.empty_like(sh_rest)
+        L.check(_timed("raster_bwd", lib.dnr_raster_bwd, C.byref(a), st), "dnr_raster_bwd")
+        sink = ctx.grad_sink
+        if sink is not None:
+            # write straight into the caller's (pre-zeroed, e.g. flat all-reduce bucket) gradient buffers
+            a.flags |= L.FLAG_ACCUMULATE
+            v_means, v_quats, v_scales = sink["means"], sink["quats"], sink["scales"]
+            v_opac, v_sh_dc, v_sh_rest = sink["opacities"], sink["features_dc"], sink["features_rest"]
+        else:
+            v_means = torch.empty_like(means)
+            v_quats = torch.empty_like(quats)
+            v_scales = torch.empty_like(scales)
+            v_opac = torch.empty_like(opac)
+            v_sh_dc = torch.empty_like(sh_dc)
+            v_sh_rest = torch.empty_like(sh_rest)
         v_m2d = torch.empty(n, 2, **f32)
         v_m2d_abs = torch.empty(n, 2, **f32)
         _set(a, v_means=v_means, v_quats=v_quats, v_scales=v_scales, v_opacities=v_opac, v_sh_dc=v_sh_dc,
              v_sh_rest=v_sh_rest if ctx.sh_bases > 1 else None, v_means2d=v_m2d, v_means2d_abs=v_m2d_abs)
-        L.check(lib.dnr_project_bwd(C.byref(a), st), "dnr_project_bwd")
+        L.check(_timed("project_bwd", lib.dnr_project_bwd, C.byref(a), st), "dnr_project_bwd")
         # what nerfstudio's after_train reads: self.xys.grad / self.xys.absgrad (dn_model.py:517-519)
         S["means2d"].grad = v_m2d
         S["means2d"].absgrad = v_m2d_abs
+        if sink is not None:
+            return (None,) * 11
         return (v_means, v_quats, v_scales, v_opac.view(ctx.opac_shape), v_sh_dc, v_sh_rest, None, None, None, None, None)
 
 
@@ -232,7 +257,7 @@ def dn_rasterize(
     viewmat: Tensor, K: Tensor, width: int, height: int, *, sh_degree: int = 3, near_plane: float = 0.01,
     far_plane: float = 1e10, eps2d: float = 0.3, antialiased: bool = False,
     background: Sequence[float] = (0.0, 0.0, 0.0), render_normals: bool = True, c2w: Optional[Tensor] = None,
-    activated: bool = False, surface_normal: bool = True,
+    activated: bool = False, surface_normal: bool = True, grad_sink: Optional[dict] = None,
 ) -> RasterOutput:
     """Renders one view.  Inputs are the reference's RAW gauss_params (log-scales, opacity logits,
     un-normalised wxyz quats, SH coefficients split as features_dc / features_rest) unless
@@ -245,6 +270,10 @@ def dn_rasterize(
                               far_plane=far_plane, eps2d=eps2d, antialiased=antialiased, render_normals=render_normals,
                               activated=activated, background=bg, surface_normal=surface_normal)
     info: dict = {}
+    if grad_sink is not None:
+        # dict with fp32 contiguous buffers shaped like the six parameters (keys: means, quats, scales, opacities,
+        # features_dc, features_rest); the backward ACCUMULATES into them and autograd sees no gradient.
+        info["grad_sink"] = grad_sink
     outs = _DnRasterize.apply(means, quats, scales, opacities, sh_dc, sh_rest, viewmat, K, c2w, settings, info)
     return RasterOutput(*outs, info)
 

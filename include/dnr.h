@@ -134,12 +134,11 @@ typedef struct DnrArgs {
   const float* gt_depth;  /* [H,W] */
   const float* gt_normal; /* [H,W,3] */
   const float* gt_rgb;    /* [H,W,3] */
-  float* loss_partials;   /* [8] fp32 accumulators, see dnr_loss_fwd */
+  float* loss_partials;   /* [12] fp32 accumulators + results, see dnr_loss_fwd */
+  const float* v_loss;    /* [1] device scalar: upstream gradient of the regulariser (NULL = 1) */
   float depth_lambda, depth_tolerance;
   int32_t depth_loss_type; /* 0 none, 1 EdgeAwareLogL1, 2 LogL1, 3 L1, 4 MSE */
   int32_t use_normal_loss;
-  float v_loss;            /* upstream gradient of the scalar regulariser */
-  float reserved2;
 } DnrArgs;
 
 int dnr_version(void);
@@ -163,12 +162,19 @@ int dnr_normal_from_depth(const DnrArgs* a, void* stream);
 int dnr_raster_bwd(const DnrArgs* a, void* stream);
 int dnr_project_bwd(const DnrArgs* a, void* stream);
 
-/* DNRegularization depth + normal terms on the rendered maps.  loss_partials (zeroed by the call):
+/* DNRegularization depth + normal terms on rendered maps: pred depth in a->out_depth, pred normal in
+ * a->out_normal.  loss_partials (zeroed by the call):
  * [0] sum_x  [1] count_x  [2] sum_y  [3] count_y  (depth term; for non edge-aware types only x is used)
- * [4] sum |n - n_gt|   [5] sum |dW n|   [6] sum |dH n|.   dnr_loss_bwd writes d(loss)/d(depth),
- * d(loss)/d(normal) into a->v_depth / a->v_normal style buffers passed as out pointers. */
+ * [4] sum |n - n_gt|   [5] sum |dW n|   [6] sum |dH n|
+ * [8] depth term incl. the (1 + depth_lambda) factor  [9] normal L1  [10] normal TV  [11] [8]+[9]+[10].
+ * dnr_loss_bwd writes d(loss)/d(depth) [H,W] and d(loss)/d(normal) [H,W,3] (either may be NULL). */
 int dnr_loss_fwd(const DnrArgs* a, void* stream);
 int dnr_loss_bwd(const DnrArgs* a, float* v_depth_out, float* v_normal_out, void* stream);
+
+/* DNRegularization.get_scale_loss (regularization_strategy.py:195-199): mean_i min_k exp(scales[i,k]).
+ * fwd: *loss_out (zeroed by the call) = the mean.  bwd: v_scales[N,3] = v * d(loss)/d(scales) (dense). */
+int dnr_scale_loss_fwd(const float* scales, int32_t n_gauss, float* loss_out, void* stream);
+int dnr_scale_loss_bwd(const float* scales, int32_t n_gauss, const float* v_loss, float* v_scales, void* stream);
 
 #ifdef __cplusplus
 }

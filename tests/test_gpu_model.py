@@ -1,0 +1,158 @@
+"""GPU tests of the reference-facing surface: DNSplatterModel.get_outputs / get_loss_dict and
+DNRegularization against the oracle (whose loss code is pinned to the reference's by tests/golden)."""
+import pytest
+import torch
+
+from tests.helpers import frac_close, oracle_outputs, scene_and_camera
+
+pytestmark = pytest.mark.gpu
+needs_cuda = pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")
+
+
+def _model(params, **cfg_kw):
+    from dn_splatter_b200.dn_model import DNSplatterModelConfig
+
+    cfg = DNSplatterModelConfig(random_init=True, num_random=16, background_color="black", **cfg_kw)
+    m = cfg.setup(device="cuda")
+    m.load_gaussians(params)
+    m.background_color = torch.tensor([0.1490, 0.1647, 0.2157])
+    m.step = 30000
+    m.train()
+    return m
+
+
+def _camera(cam):
+    from dn_splatter_b200.cameras import Cameras
+
+    return Cameras(cam["c2w"][None].cuda(), cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["width"], cam["height"],
+                   metadata={"cam_idx": 7})
+
+
+def _batch(H, W, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    depth = 2 + 6 * torch.rand(H, W, 1, generator=g)
+    depth[torch.rand(H, W, 1, generator=g) < 0.1] = 0.0
+    return {"image": (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8), "mono_depth": depth,
+            "normal": torch.rand(H, W, 3, generator=g)}
+
+
+@needs_cuda
+def test_get_outputs_keys_shapes_and_side_outputs():
+    params, cam = scene_and_camera(800, 112, 96)
+    m = _model(params)
+    out = m.get_outputs(_camera(cam))
+    assert set(out) == {"rgb", "depth", "normal", "surface_normal", "accumulation", "background"}
+    H, W = 96, 112
+    assert out["rgb"].shape == (H, W, 3) and out["depth"].shape == (H, W, 1) and out["normal"].shape == (H, W, 3)
+    assert out["surface_normal"].shape == (H, W, 3) and out["accumulation"].shape == (H, W, 1)
+    assert m.xys.shape == (1, 800, 2) and m.radii.shape == (800,) and m.radii.dtype == torch.int32
+    assert m.depths.shape == (1, 800) and m.conics.shape == (1, 800, 3) and m.num_tiles_hit.shape == (1, 800)
+    assert m.last_size == (H, W) and m.camera_idx == 7
+    assert torch.equal(m.vis_indices, torch.where(m.radii > 0)[0])
+    assert m.get_outputs("not a camera") == {}
+    _, ref = oracle_outputs(params, cam)
+    for k, kk in (("rgb", "rgb"), ("normal", "normal"), ("accumulation", "accumulation")):
+        frac, mx = frac_close(out[k], ref[kk], atol=1e-4)
+        assert frac > 0.999, (k, frac, mx)
+    torch.testing.assert_close(m.normals.detach().cpu(), ref["gauss_normals"], rtol=1e-4, atol=1e-5)
+
+
+@needs_cuda
+@pytest.mark.parametrize("depth_type", ["EdgeAwareLogL1", "LogL1", "L1", "MSE"])
+def test_loss_dict_matches_oracle_and_gradients_flow(depth_type):
+    from dn_splatter_b200.losses import DepthLossType
+    from oracle import dn_ref
+
+    params, cam = scene_and_camera(900, 128, 80, view=2)
+    H, W = 80, 128
+    batch = _batch(H, W)
+    m = _model(params, use_depth_loss=True, depth_lambda=0.2, depth_loss_type=DepthLossType(depth_type if depth_type != "MSE" else "mse"),
+               ssim_lambda=0.0)
+    out = m.get_outputs(_camera(cam))
+    ld = m.get_loss_dict(out, dict(batch))
+    assert set(ld) == {"main_loss", "scale_reg"}
+    ld["main_loss"].backward()
+    # oracle
+    p, ref = oracle_outputs(params, cam, requires_grad=True)
+    gt_img = (batch["image"].float() / 255.0)
+    rgb_loss = (gt_img - ref["rgb"]).abs().mean()
+    reg = dn_ref.dn_regularization(ref["depth"], batch["mono_depth"], ref["normal"], batch["normal"], p["scales"],
+                                   gt_img.clamp(min=10 / 255.0), depth_lambda=0.2, depth_loss_type=depth_type)
+    want = rgb_loss + reg
+    want.backward()
+    assert abs(float(ld["main_loss"]) - float(want)) <= 2e-4 * max(1.0, abs(float(want))), (float(ld["main_loss"]), float(want))
+    for k in ("means", "quats", "scales", "opacities", "features_dc", "features_rest"):
+        got, w = m.gauss_params[k].grad.cpu(), p[k].grad
+        rel = float((got - w).norm() / (w.norm() + 1e-20))
+        assert rel < 5e-3, f"{k}: {rel:.3e}"
+    assert m.xys_flat.absgrad is not None and m.xys_flat.grad is not None
+
+
+@needs_cuda
+def test_flat_grad_bucket_equals_autograd_path():
+    params, cam = scene_and_camera(700, 96, 96, view=1)
+    batch = _batch(96, 96)
+    from dn_splatter_b200.losses import DepthLossType
+
+    kw = dict(use_depth_loss=True, depth_lambda=0.2, depth_loss_type=DepthLossType.EdgeAwareLogL1, ssim_lambda=0.2)
+    a, b = _model(params, **kw), _model(params, **kw)
+    bucket = b.enable_flat_grads()
+    bucket.zero_()
+    for m in (a, b):
+        out = m.get_outputs(_camera(cam))
+        ld = m.get_loss_dict(out, dict(batch))
+        (ld["main_loss"] + ld["scale_reg"]).backward()
+    for k in ("means", "quats", "scales", "opacities", "features_dc", "features_rest"):
+        torch.testing.assert_close(b.gauss_params[k].grad, a.gauss_params[k].grad, rtol=2e-4, atol=1e-7)
+        assert b.gauss_params[k].grad.data_ptr() == bucket.views[k].data_ptr()
+
+
+@needs_cuda
+def test_normal_from_depth_image_matches_reference_goldens(golden_dir):
+    import glob
+    import os
+
+    import numpy as np
+
+    from dn_splatter_b200.utils.normal_utils import normal_from_depth_image
+
+    for f in sorted(glob.glob(os.path.join(golden_dir, "dn_reference_*.npz"))):
+        z = np.load(f)
+        d = torch.from_numpy(z["in_pred_depth"]).cuda()
+        fx, fy, cx, cy = [float(v) for v in z["in_intr"]]
+        H, W, _ = d.shape
+        n = normal_from_depth_image(d, fx, fy, cx, cy, (W, H), torch.eye(4).cuda(), d.device)
+        torch.testing.assert_close(n.cpu(), torch.from_numpy(z["out_normal_from_depth"]), rtol=1e-4, atol=2e-5)
+
+
+@needs_cuda
+def test_dn_regularization_matches_reference_goldens(golden_dir):
+    import glob
+    import os
+
+    import numpy as np
+
+    from dn_splatter_b200.losses import DepthLoss, DepthLossType
+    from dn_splatter_b200.regularization_strategy import DNRegularization
+
+    for f in sorted(glob.glob(os.path.join(golden_dir, "dn_reference_*.npz"))):
+        z = {k: torch.from_numpy(v).cuda() for k, v in np.load(f).items()}
+        for key, lam, t in (("dn_reg_lambda0.2", 0.2, None), ("dn_reg_lambda0.5", 0.5, None),
+                            ("dn_reg_LogL1", 0.2, DepthLossType.LogL1), ("dn_reg_L1", 0.2, DepthLossType.L1),
+                            ("dn_reg_mse", 0.2, DepthLossType.MSE), ("dn_reg_nodepth", 0.2, "none")):
+            reg = DNRegularization(depth_lambda=lam).cuda()
+            if t == "none":
+                reg.depth_loss = None
+            elif t is not None:
+                reg.depth_loss_type, reg.depth_loss = t, DepthLoss(t)
+            pd = z["in_pred_depth"].clone().requires_grad_(True)
+            pn = z["in_pred_normal"].clone().requires_grad_(True)
+            sc = z["in_scales"].clone().requires_grad_(True)
+            v = reg(pred_depth=pd, gt_depth=z["in_gt_depth"], pred_normal=pn, gt_normal=z["in_gt_normal"], scales=sc,
+                    gt_img=z["in_gt_img"])
+            torch.testing.assert_close(v, z["out_" + key], rtol=2e-5, atol=1e-6)
+            if key == "dn_reg_lambda0.2":
+                v.backward()
+                torch.testing.assert_close(pd.grad, z["out_grad_pred_depth"], rtol=1e-4, atol=1e-8)
+                torch.testing.assert_close(pn.grad, z["out_grad_pred_normal"], rtol=1e-4, atol=1e-8)
+                torch.testing.assert_close(sc.grad, z["out_grad_scales"], rtol=1e-4, atol=1e-8)

@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--no-normals", action="store_true", help="BASELINE config C2 literal: RGB+depth only")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--cpu-crop", default="384x216")
+    ap.add_argument("--cpu-crop", default="256x144")
+    ap.add_argument("--sync", action="store_true", help="read the intersection count back every view (host sync)")
     return ap.parse_args()
 
 
@@ -112,6 +113,7 @@ def build_workload(args, device, normals: bool):
     cfg = DNSplatterModelConfig(
         random_init=True, num_random=16, use_depth_loss=True, depth_lambda=0.2, depth_loss_type=DepthLossType.EdgeAwareLogL1,
         predict_normals=normals, use_normal_loss=normals, normal_supervision="mono", ssim_lambda=0.0, background_color="black",
+        sync_free=not args.sync,
     )
     model = cfg.setup(device=device)
     model.load_gaussians(make_scene(args.n_gauss, seed=0))
@@ -167,7 +169,9 @@ def cpu_reference_sample(args, normals: bool, crop: str):
     from dn_splatter_b200.synthetic import BACKGROUND, make_scene, ring_cameras
     from oracle import dn_ref
 
-    cores = os.cpu_count() or 1
+    # torch's intra-op pool thrashes on the per-tile tensors beyond ~16 threads (measured: 128 threads are 100x slower
+    # than 8 on this path), so the port uses at most 16 of the host's cores and reports that number.
+    cores = min(os.cpu_count() or 1, 16)
     torch.set_num_threads(cores)
     cw, ch = (int(x) for x in crop.split("x"))
     cw, ch = min(cw, args.width), min(ch, args.height)
@@ -312,7 +316,7 @@ def main():
         R.STAGE_EVENTS = None
         out = model.raster_out
         info = out.info
-        I = int(info["n_isects"])
+        I = int(info["n_isects_dev"])
         to = info["tile_offsets"].long()
         tiles_x = info["tile_width"]
         H, W = args.height, args.width

@@ -9,7 +9,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdnr_b200.so")
 
-FLAG_ACTIVATED, FLAG_ANTIALIASED, FLAG_NORMALS, FLAG_ACCUMULATE = 1, 2, 4, 8
+FLAG_ACTIVATED, FLAG_ANTIALIASED, FLAG_NORMALS, FLAG_ACCUMULATE, FLAG_EXACT_LISTS = 1, 2, 4, 8, 16
 REC_FLOATS, REC_FLOATS_N, GRAD_FLOATS = 12, 16, 16
 DEPTH_LOSS_TYPES = {None: 0, "EdgeAwareLogL1": 1, "LogL1": 2, "L1": 3, "MSE": 4}
 
@@ -28,8 +28,8 @@ class DnrArgs(C.Structure):
         ("viewmat", _p), ("K", _p), ("c2w", _p),
         ("means", _p), ("quats", _p), ("scales", _p), ("opacities", _p), ("sh_dc", _p), ("sh_rest", _p),
         ("radii", _p), ("means2d", _p), ("depths", _p), ("conics", _p), ("opac_act", _p), ("compensations", _p),
-        ("colors", _p), ("normals_world", _p), ("tiles_per_gauss", _p), ("depth_keys", _p), ("records", _p),
-        ("ws_scan", _p), ("ws_sort", _p), ("flatten_ids", _p), ("tile_offsets", _p),
+        ("colors", _p), ("normals_world", _p), ("tiles_per_gauss", _p), ("depth_keys", _p), ("records", _p), ("cull_lim", _p),
+        ("ws_scan", _p), ("ws_sort", _p), ("flatten_ids", _p), ("tile_offsets", _p), ("n_isects_dev", _p),
         ("out_rgb", _p), ("out_depth", _p), ("out_alpha", _p), ("out_normal", _p), ("out_surface_normal", _p),
         ("last_ids", _p), ("normal_norm", _p), ("clamp_mask", _p), ("depth_max", _p),
         ("v_rgb", _p), ("v_depth", _p), ("v_normal", _p), ("v_alpha", _p), ("grad_records", _p),

@@ -7,13 +7,16 @@
 // B200-first formulation (same result, ~4x less sort traffic than sorting I 64-bit keys):
 //   1. sort the N Gaussians once by depth bits (32-bit keys, N items; culled = 0xFFFFFFFF go last);
 //      a stable sort keeps equal depths in ascending Gaussian index;
-//   2. exclusive-scan the tile counts in that depth order -> where each Gaussian emits;
-//   3. emit (tile_id, gaussian_id) pairs in depth order — one warp per Gaussian, coalesced;
+//   2. count, per Gaussian (one warp each, lanes over its tile box), the tiles it can really reach:
+//      a conservative exact ellipse/rectangle test (dnr_rect_hit) drops the ~55 % of bbox tiles in which no
+//      pixel can reach alpha >= 1/255 — those pairs would be skipped by every pixel anyway, so the rendered
+//      images are bit-identical; DNR_FLAG_EXACT_LISTS keeps gsplat's full bbox lists for parity checks;
+//      exclusive-scan the counts in depth order -> where each Gaussian emits;
+//   3. emit (tile_id, gaussian_id) pairs in depth order — one warp per Gaussian, ballot-compacted, coalesced;
 //   4. STABLE radix sort of the I pairs on the tile-id bits only (13-15 bits, 16-bit keys): within a
 //      tile the depth order of step 1 survives, so the list equals gsplat's sort by (tile, depth, id);
 //   5. tile offsets from the sorted tile ids.
 #include <cub/cub.cuh>
-#include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 
 #include "common.cuh"
@@ -22,13 +25,8 @@ namespace {
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-struct GatherCounts {
-  const int32_t* tiles_per_gauss;
-  const int32_t* order;
-  int32_t n;
-  __host__ __device__ __forceinline__ int64_t operator()(int32_t i) const {
-    return i < n ? (int64_t)tiles_per_gauss[order[i]] : (int64_t)0;
-  }
+struct ToI64 {
+  __host__ __device__ __forceinline__ int64_t operator()(int32_t v) const { return (int64_t)v; }
 };
 
 __global__ void iota_kernel(int32_t* out, int32_t n) {
@@ -40,6 +38,7 @@ struct ScanWs {
   uint32_t* keys_sorted;
   int32_t* order;
   int32_t* iota;
+  int32_t* counts;       // [N+1] tiles really touched, in depth order (last = 0)
   int64_t* isect_start;  // [N+1]
   void* cub_temp;
   size_t cub_bytes;
@@ -53,12 +52,12 @@ ScanWs carve_scan(void* base, int32_t n) {
   w.keys_sorted = (uint32_t*)(p + off); off += align_up((size_t)n * 4);
   w.order = (int32_t*)(p + off); off += align_up((size_t)n * 4);
   w.iota = (int32_t*)(p + off); off += align_up((size_t)n * 4);
+  w.counts = (int32_t*)(p + off); off += align_up((size_t)(n + 1) * 4);
   w.isect_start = (int64_t*)(p + off); off += align_up((size_t)(n + 1) * 8);
   size_t sort_bytes = 0, scan_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
                                   (int32_t*)nullptr, n, 0, 32);
-  GatherCounts f{nullptr, nullptr, n};
-  auto it = thrust::make_transform_iterator(thrust::make_counting_iterator<int32_t>(0), f);
+  auto it = thrust::make_transform_iterator((const int32_t*)nullptr, ToI64());
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, it, (int64_t*)nullptr, n + 1);
   w.cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
   w.cub_temp = (void*)(p + off); off += align_up(w.cub_bytes);
@@ -100,7 +99,39 @@ inline int tile_bits_for(int n_tiles) {
   return b;
 }
 
-// One warp per depth-sorted Gaussian; lanes stride over its tile box (row-major, as gsplat emits).
+// Pixel-centre rectangle of tile (tx,ty), clipped to the image.
+__device__ __forceinline__ bool tile_reachable(const DnrArgs& a, int g, float mx, float my, int tx, int ty) {
+  const float x0 = (float)(tx * DNR_TILE) + 0.5f, y0 = (float)(ty * DNR_TILE) + 0.5f;
+  const float x1 = fminf((float)(tx * DNR_TILE + DNR_TILE - 1), (float)(a.width - 1)) + 0.5f;
+  const float y1 = fminf((float)(ty * DNR_TILE + DNR_TILE - 1), (float)(a.height - 1)) + 0.5f;
+  return dnr_rect_hit(mx, my, a.conics[g * 3 + 0], a.conics[g * 3 + 1], a.conics[g * 3 + 2], a.cull_lim[g], x0, x1, y0, y1);
+}
+
+// One warp per depth-sorted Gaussian: number of tiles of its box that it can really reach.
+__global__ void __launch_bounds__(256) count_kernel(const DnrArgs a, const int32_t* __restrict__ order,
+                                                   int32_t* __restrict__ counts, int tiles_x, int tiles_y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp > a.n_gauss) return;
+  if (warp == a.n_gauss) { if (lane == 0) counts[warp] = 0; return; }
+  const int g = order[warp];
+  const int radius = a.radii[g];
+  if (radius <= 0) { if (lane == 0) counts[warp] = 0; return; }
+  if (a.flags & DNR_FLAG_EXACT_LISTS) { if (lane == 0) counts[warp] = a.tiles_per_gauss[g]; return; }
+  const float mx = a.means2d[g * 2 + 0], my = a.means2d[g * 2 + 1];
+  int x0, y0, x1, y1;
+  dnr_tile_box(mx, my, radius, tiles_x, tiles_y, x0, y0, x1, y1);
+  const int nx = x1 - x0, total = nx * (y1 - y0);
+  int cnt = 0;
+  for (int k = lane; k < total; k += 32) cnt += tile_reachable(a, g, mx, my, x0 + k % nx, y0 + k / nx) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) counts[warp] = cnt;
+}
+
+// One warp per depth-sorted Gaussian; lanes stride over its tile box (row-major, as gsplat emits), survivors
+// are ballot-compacted so the row-major order is kept.  Entries past the capacity are dropped (the caller sees
+// n_isects_dev > capacity and retries).
 template <typename KeyT>
 __global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_t* __restrict__ order,
                                                   const int64_t* __restrict__ isect_start, KeyT* __restrict__ keys,
@@ -111,21 +142,46 @@ __global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_
   const int64_t start = isect_start[warp];
   const int count = (int)(isect_start[warp + 1] - start);
   if (count == 0) return;
+  const int64_t cap = a.n_isects;
   const int g = order[warp];
+  const float mx = a.means2d[g * 2 + 0], my = a.means2d[g * 2 + 1];
   int x0, y0, x1, y1;
-  dnr_tile_box(a.means2d[g * 2 + 0], a.means2d[g * 2 + 1], a.radii[g], tiles_x, tiles_y, x0, y0, x1, y1);
-  const int nx = x1 - x0;
-  for (int k = lane; k < count; k += 32) {
+  dnr_tile_box(mx, my, a.radii[g], tiles_x, tiles_y, x0, y0, x1, y1);
+  const int nx = x1 - x0, total = nx * (y1 - y0);
+  const bool exact = (a.flags & DNR_FLAG_EXACT_LISTS) != 0;
+  int written = 0;
+  for (int k0 = 0; k0 < total; k0 += 32) {
+    const int k = k0 + lane;
     const int ty = y0 + k / nx, tx = x0 + k % nx;
-    keys[start + k] = (KeyT)(ty * tiles_x + tx);
-    gids[start + k] = g;
+    const bool hit = (k < total) && (exact || tile_reachable(a, g, mx, my, tx, ty));
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int64_t dst = start + written + __popc(m & ((1u << lane) - 1u));
+      if (dst < cap) {
+        keys[dst] = (KeyT)(ty * tiles_x + tx);
+        gids[dst] = g;
+      }
+    }
+    written += __popc(m);
+  }
+}
+
+// Pads [count, capacity) with the maximal key so a fixed-size sort leaves them at the end.
+template <typename KeyT>
+__global__ void __launch_bounds__(256) pad_kernel(KeyT* __restrict__ keys, int32_t* __restrict__ gids,
+                                                 const int64_t* __restrict__ n_isects_dev, int64_t cap) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap && i >= *n_isects_dev) {
+    keys[i] = (KeyT)~(KeyT)0;
+    gids[i] = 0;
   }
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(256) offsets_kernel(const KeyT* __restrict__ keys, int64_t n_isects, int n_tiles,
-                                                     int32_t* __restrict__ offsets) {
+__global__ void __launch_bounds__(256) offsets_kernel(const KeyT* __restrict__ keys, const int64_t* __restrict__ n_isects_dev,
+                                                     int64_t cap, int n_tiles, int32_t* __restrict__ offsets) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_isects = min(*n_isects_dev, cap);
   if (n_isects == 0) {
     if (i <= n_tiles) offsets[i] = 0;
     return;
@@ -147,19 +203,23 @@ template <typename KeyT>
 int bin_sort_impl(const DnrArgs* a, cudaStream_t s, int n_tiles, int tile_bits) {
   const int tiles_x = dnr_tiles_x(a), tiles_y = dnr_tiles_y(a);
   ScanWs sw = carve_scan(a->ws_scan, a->n_gauss);
-  SortWs<KeyT> w = carve_sort<KeyT>(a->ws_sort, a->n_isects, tile_bits);
-  const int64_t I = a->n_isects;
-  if (I > 0) {
+  const int64_t cap = a->n_isects;
+  SortWs<KeyT> w = carve_sort<KeyT>(a->ws_sort, cap, tile_bits);
+  if (cap > 0) {
     const int64_t threads = (int64_t)a->n_gauss * 32;
     emit_kernel<KeyT><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(*a, sw.order, sw.isect_start, w.keys_in, w.gids_in,
                                                                           tiles_x, tiles_y);
     DNR_CHECK_LAUNCH();
+    pad_kernel<KeyT><<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(w.keys_in, w.gids_in, a->n_isects_dev, cap);
+    DNR_CHECK_LAUNCH();
     size_t bytes = w.cub_bytes;
+    // the padding key has all bits set: sort one bit more than the tile ids need so it lands behind every tile
+    const int end_bit = min(tile_bits + 1, (int)(8 * sizeof(KeyT)));
     DNR_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, bytes, (const KeyT*)w.keys_in, w.keys_out,
-                                             (const int32_t*)w.gids_in, a->flatten_ids, I, 0, tile_bits, s));
+                                             (const int32_t*)w.gids_in, a->flatten_ids, cap, 0, end_bit, s));
   }
-  const int64_t n = I > 0 ? I : (int64_t)n_tiles + 1;
-  offsets_kernel<KeyT><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.keys_out, I, n_tiles, a->tile_offsets);
+  const int64_t n = cap > (int64_t)n_tiles + 1 ? cap : (int64_t)n_tiles + 1;
+  offsets_kernel<KeyT><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.keys_out, a->n_isects_dev, cap, n_tiles, a->tile_offsets);
   DNR_CHECK_LAUNCH();
   return 0;
 }
@@ -172,9 +232,10 @@ extern "C" size_t dnr_bin_scan_workspace_bytes(int32_t n_gauss) {
 }
 
 extern "C" int dnr_bin_scan(const DnrArgs* a, void* stream, int64_t* n_isects_host) {
-  if (!a || !n_isects_host) return DNR_E_NULL;
-  if (a->n_gauss <= 0) return DNR_E_SIZE;
-  if (!a->ws_scan || !a->depth_keys || !a->tiles_per_gauss) return DNR_E_NULL;
+  if (!a) return DNR_E_NULL;
+  if (a->n_gauss <= 0 || a->width <= 0 || a->height <= 0) return DNR_E_SIZE;
+  if (!a->ws_scan || !a->depth_keys || !a->tiles_per_gauss || !a->n_isects_dev || !a->radii || !a->means2d) return DNR_E_NULL;
+  if (!(a->flags & DNR_FLAG_EXACT_LISTS) && (!a->conics || !a->cull_lim)) return DNR_E_NULL;
   cudaStream_t s = (cudaStream_t)stream;
   const int32_t n = a->n_gauss;
   ScanWs w = carve_scan(a->ws_scan, n);
@@ -183,15 +244,22 @@ extern "C" int dnr_bin_scan(const DnrArgs* a, void* stream, int64_t* n_isects_ho
   size_t bytes = w.cub_bytes;
   DNR_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, bytes, (const uint32_t*)a->depth_keys, w.keys_sorted,
                                            (const int32_t*)w.iota, w.order, n, 0, 32, s));
-  GatherCounts f{a->tiles_per_gauss, w.order, n};
-  auto it = thrust::make_transform_iterator(thrust::make_counting_iterator<int32_t>(0), f);
+  {
+    const int64_t threads = ((int64_t)n + 1) * 32;
+    count_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(*a, w.order, w.counts, dnr_tiles_x(a), dnr_tiles_y(a));
+    DNR_CHECK_LAUNCH();
+  }
+  auto it = thrust::make_transform_iterator((const int32_t*)w.counts, ToI64());
   bytes = w.cub_bytes;
   DNR_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, bytes, it, w.isect_start, n + 1, s));
-  int64_t total = 0;
-  DNR_CUDA(cudaMemcpyAsync(&total, w.isect_start + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  DNR_CUDA(cudaStreamSynchronize(s));
-  *n_isects_host = total;
-  if (total > 0x7FFFFFFFLL) return DNR_E_OVERFLOW;
+  DNR_CUDA(cudaMemcpyAsync(a->n_isects_dev, w.isect_start + n, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  if (n_isects_host) {
+    int64_t total = 0;
+    DNR_CUDA(cudaMemcpyAsync(&total, w.isect_start + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    DNR_CUDA(cudaStreamSynchronize(s));
+    *n_isects_host = total;
+    if (total > 0x7FFFFFFFLL) return DNR_E_OVERFLOW;
+  }
   return 0;
 }
 
@@ -207,7 +275,8 @@ extern "C" int dnr_bin_sort(const DnrArgs* a, void* stream) {
   if (!a) return DNR_E_NULL;
   if (a->n_gauss <= 0 || a->n_isects < 0 || a->width <= 0 || a->height <= 0) return DNR_E_SIZE;
   if (a->n_isects > 0x7FFFFFFFLL) return DNR_E_OVERFLOW;
-  if (!a->ws_scan || !a->ws_sort || !a->tile_offsets || !a->means2d || !a->radii) return DNR_E_NULL;
+  if (!a->ws_scan || !a->ws_sort || !a->tile_offsets || !a->means2d || !a->radii || !a->n_isects_dev) return DNR_E_NULL;
+  if (!(a->flags & DNR_FLAG_EXACT_LISTS) && (!a->conics || !a->cull_lim)) return DNR_E_NULL;
   if (a->n_isects > 0 && !a->flatten_ids) return DNR_E_NULL;
   const int n_tiles = dnr_tiles_x(a) * dnr_tiles_y(a);
   const int bits = tile_bits_for(n_tiles);

@@ -39,6 +39,49 @@ __device__ __forceinline__ void dnr_tile_box(float mx, float my, int radius, int
   y1 = min(max((int)ceilf(tcy + r), 0), tiles_y);
 }
 
+// Conservative precise-hit test used when emitting intersections: can the Gaussian (centre m, conic A,B,C)
+// reach sigma <= lim anywhere on the pixel-centre rectangle [x0,x1]x[y0,y1]?  sigma is a convex quadratic, so
+// its minimum over the rectangle is 0 (centre inside) or lies on the edge(s) facing the centre.
+__device__ __forceinline__ bool dnr_rect_hit(float mx, float my, float A, float B, float C, float lim, float x0,
+                                             float x1, float y0, float y1) {
+  const bool in_x = (mx >= x0) && (mx <= x1), in_y = (my >= y0) && (my <= y1);
+  if (in_x && in_y) return true;
+  // each candidate is lowered by a bound on its own rounding error (terms can cancel for needle-like splats)
+  float qmin = 3.0e38f;
+  if (!in_x) {
+    const float dx = mx - (mx < x0 ? x0 : x1);
+    const float ys = fminf(fmaxf(my + B * dx / C, y0), y1);
+    const float dy = my - ys;
+    const float t0 = A * dx * dx, t1 = C * dy * dy, t2 = B * dx * dy;
+    qmin = 0.5f * (t0 + t1) + t2 - 4e-6f * (fabsf(t0) + fabsf(t1) + fabsf(t2));
+  }
+  if (!in_y) {
+    const float dy = my - (my < y0 ? y0 : y1);
+    const float xs = fminf(fmaxf(mx + B * dy / A, x0), x1);
+    const float dx = mx - xs;
+    const float t0 = A * dx * dx, t1 = C * dy * dy, t2 = B * dx * dy;
+    qmin = fminf(qmin, 0.5f * (t0 + t1) + t2 - 4e-6f * (fabsf(t0) + fabsf(t1) + fabsf(t2)));
+  }
+  return qmin <= lim;
+}
+
+// log2-domain exponent of a splat at offset (dx,dy): records hold a' = -0.5*log2(e)*A, b' = -log2(e)*B,
+// c' = -0.5*log2(e)*C, so alpha = opac * 2^power.  Fixed rounding order, shared by the forward and backward
+// kernels so that both take the same skip/stop branches for every (pixel, Gaussian) pair.
+__device__ __forceinline__ float dnr_power2(float a, float b, float c, float dx, float dy) {
+  const float t1 = __fmaf_rn(a, dx, __fmul_rn(b, dy));
+  const float t2 = __fmul_rn(c, dy);
+  return __fmaf_rn(dx, t1, __fmul_rn(dy, t2));
+}
+__device__ __forceinline__ float dnr_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+#define DNR_LOG2E 1.4426950408889634f
+#define DNR_LN2 0.6931471805599453f
+#define DNR_CULL_MARGIN 0.1f /* in sigma units: a tile is dropped only if alpha_max < e^-0.1 / 255 */
+
 // ---- mbarrier / bulk-copy (TMA, 1-D) primitives -------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

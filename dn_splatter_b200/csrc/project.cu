@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const DnrArgs a) {
     a.depths[i] = 0.f;
     a.conics[i * 3 + 0] = 0.f; a.conics[i * 3 + 1] = 0.f; a.conics[i * 3 + 2] = 0.f;
     a.opac_act[i] = 0.f;
+    if (a.cull_lim) a.cull_lim[i] = -1.0f;
     if (a.compensations) a.compensations[i] = 0.f;
     a.colors[i * 3 + 0] = 0.f; a.colors[i * 3 + 1] = 0.f; a.colors[i * 3 + 2] = 0.f;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -290,6 +291,8 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const DnrArgs a) {
   const float conA = g.c * inv_det, conB = -(g.b * inv_det), conC = g.a * inv_det;
   float op = a.opacities[i];
   if (!(a.flags & DNR_FLAG_ACTIVATED)) op = 1.0f / (1.0f + expf(-op));
+  // largest sigma at which a pixel can still pass alpha >= 1/255 (pre-compensation opacity: conservative for both modes)
+  if (a.cull_lim) a.cull_lim[i] = logf(255.0f * op) + DNR_CULL_MARGIN;
   if (a.flags & DNR_FLAG_ANTIALIASED) op = op * g.comp;
 
   // SH colour: clamp_min(SH(dir) + 0.5, 0)
@@ -327,10 +330,13 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const DnrArgs a) {
   a.opac_act[i] = op;
   if (a.compensations) a.compensations[i] = g.comp;
   a.colors[i * 3 + 0] = col[0]; a.colors[i * 3 + 1] = col[1]; a.colors[i * 3 + 2] = col[2];
-  rec[0] = make_float4(g.mx, g.my, conA, conB);
-  rec[1] = make_float4(conC, op, col[0], col[1]);
-  rec[2] = make_float4(col[2], g.mc[2], nc[0], nc[1]);
-  if (NORMALS) rec[3] = make_float4(nc[2], 0.f, 0.f, 0.f);
+  // raster record: log2-domain conic (see dnr_power2), opacity, and -log2(255*op) - slack: the cheap in-loop
+  // pre-test "power < nthr => alpha < 1/255" (the exact alpha test still decides; 1e-3 slack keeps it conservative)
+  const float nthr = -log2f(255.0f * op) - 1e-3f;
+  rec[0] = make_float4(g.mx, g.my, (-0.5f * DNR_LOG2E) * conA, (-DNR_LOG2E) * conB);
+  rec[1] = make_float4((-0.5f * DNR_LOG2E) * conC, op, nthr, 0.f);
+  rec[2] = make_float4(col[0], col[1], col[2], g.mc[2]);
+  if (NORMALS) rec[3] = make_float4(nc[0], nc[1], nc[2], 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -87,20 +87,21 @@ __global__ void __launch_bounds__(256) raster_fwd_kernel(const DnrArgs a, int ti
     const float4* r4 = reinterpret_cast<const float4*>(recs[stage]);
     const int base = start + c * CH;
     for (int t = 0; t < n_c && !done; ++t) {
-      const float4 r0 = r4[t * (REC / 4) + 0];
-      const float4 r1 = r4[t * (REC / 4) + 1];
-      const float dx = r0.x - px, dy = r0.y - py;
-      const float sigma = 0.5f * (r0.z * dx * dx + r1.x * dy * dy) + r0.w * dx * dy;
-      const float alpha = fminf(DNR_ALPHA_MAX, r1.y * __expf(-sigma));
-      if (sigma < 0.f || alpha < DNR_ALPHA_MIN) continue;
+      const float4 q0 = r4[t * (REC / 4) + 0];  // x, y, a', b'
+      const float4 q1 = r4[t * (REC / 4) + 1];  // c', opacity, -log2(255 opacity) - slack, -
+      const float dx = q0.x - px, dy = q0.y - py;
+      const float pw = dnr_power2(q0.z, q0.w, q1.x, dx, dy);  // = -sigma * log2(e)
+      if (pw > 0.f || pw < q1.z) continue;                    // sigma < 0, or alpha certainly < 1/255
+      const float alpha = fminf(DNR_ALPHA_MAX, __fmul_rn(q1.y, dnr_ex2(pw)));
+      if (alpha < DNR_ALPHA_MIN) continue;
       const float next_T = T * (1.0f - alpha);
       if (next_T <= DNR_T_STOP) { done = true; break; }
-      const float4 r2 = r4[t * (REC / 4) + 2];
+      const float4 q2 = r4[t * (REC / 4) + 2];  // r, g, b, depth
       const float vis = alpha * T;
-      C0 += r1.z * vis; C1 += r1.w * vis; C2 += r2.x * vis; D += r2.y * vis;
+      C0 += q2.x * vis; C1 += q2.y * vis; C2 += q2.z * vis; D += q2.w * vis;
       if (NORMALS) {
-        const float4 r3 = r4[t * (REC / 4) + 3];
-        N0 += r2.z * vis; N1 += r2.w * vis; N2 += r3.x * vis;
+        const float4 q3 = r4[t * (REC / 4) + 3];  // camera-space normal
+        N0 += q3.x * vis; N1 += q3.y * vis; N2 += q3.z * vis;
       }
       last = base + t;
       T = next_T;
@@ -284,48 +285,53 @@ __global__ void __launch_bounds__(256) raster_bwd_kernel(const DnrArgs a, int ti
     for (int t = 0; t < n_c; ++t) {
       const int idx = chi - 1 - t;
       bool valid = inside && (idx <= last_id);
-      float4 r0, r1;
+      float4 q0, q1;
       float dx = 0.f, dy = 0.f, vis = 0.f, alpha = 0.f;
       if (valid) {
-        r0 = r4[t * (REC / 4) + 0];
-        r1 = r4[t * (REC / 4) + 1];
-        dx = r0.x - px; dy = r0.y - py;
-        const float sigma = 0.5f * (r0.z * dx * dx + r1.x * dy * dy) + r0.w * dx * dy;
-        vis = __expf(-sigma);
-        alpha = fminf(DNR_ALPHA_MAX, r1.y * vis);
-        if (sigma < 0.f || alpha < DNR_ALPHA_MIN) valid = false;
+        q0 = r4[t * (REC / 4) + 0];
+        q1 = r4[t * (REC / 4) + 1];
+        dx = q0.x - px; dy = q0.y - py;
+        const float pw = dnr_power2(q0.z, q0.w, q1.x, dx, dy);
+        valid = !(pw > 0.f || pw < q1.z);
+        if (valid) {
+          vis = dnr_ex2(pw);
+          alpha = fminf(DNR_ALPHA_MAX, __fmul_rn(q1.y, vis));
+          valid = !(alpha < DNR_ALPHA_MIN);
+        }
       }
       if (!__any_sync(0xffffffffu, valid)) continue;
       float v[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) v[k] = 0.f;
       if (valid) {
-        const float4 r2 = r4[t * (REC / 4) + 2];
-        const float opac = r1.y;
+        const float4 q2 = r4[t * (REC / 4) + 2];
+        const float opac = q1.y;
         const float ra = 1.0f / (1.0f - alpha);
         T *= ra;
         const float fac = alpha * T;
         v[8] = fac * vC0; v[9] = fac * vC1; v[10] = fac * vC2; v[11] = fac * vD;
-        float v_alpha_cd = (r1.z * T - b0 * ra) * vC0 + (r1.w * T - b1 * ra) * vC1 + (r2.x * T - b2 * ra) * vC2 +
-                           (r2.y * T - bD * ra) * vD + T_final * ra * va_cd;
+        float v_alpha_cd = (q2.x * T - b0 * ra) * vC0 + (q2.y * T - b1 * ra) * vC1 + (q2.z * T - b2 * ra) * vC2 +
+                           (q2.w * T - bD * ra) * vD + T_final * ra * va_cd;
         float v_alpha_n = 0.f;
-        b0 += r1.z * fac; b1 += r1.w * fac; b2 += r2.x * fac; bD += r2.y * fac;
+        b0 += q2.x * fac; b1 += q2.y * fac; b2 += q2.z * fac; bD += q2.w * fac;
         if (NORMALS) {
-          const float4 r3 = r4[t * (REC / 4) + 3];
+          const float4 q3 = r4[t * (REC / 4) + 3];
           v[12] = fac * vN0; v[13] = fac * vN1; v[14] = fac * vN2;
-          v_alpha_n = (r2.z * T - bn0 * ra) * vN0 + (r2.w * T - bn1 * ra) * vN1 + (r3.x * T - bn2 * ra) * vN2 +
+          v_alpha_n = (q3.x * T - bn0 * ra) * vN0 + (q3.y * T - bn1 * ra) * vN1 + (q3.z * T - bn2 * ra) * vN2 +
                       T_final * ra * va_n;
-          bn0 += r2.z * fac; bn1 += r2.w * fac; bn2 += r3.x * fac;
+          bn0 += q3.x * fac; bn1 += q3.y * fac; bn2 += q3.z * fac;
         }
         if (opac * vis <= DNR_ALPHA_MAX) {
           const float v_alpha_all = v_alpha_cd + v_alpha_n;
-          const float vs_cd = -opac * vis * v_alpha_cd;
+          const float vs_cd = -opac * vis * v_alpha_cd;   // d/d sigma
           const float vs_all = -opac * vis * v_alpha_all;
           v[4] = 0.5f * vs_all * dx * dx;
           v[5] = vs_all * dx * dy;
           v[6] = 0.5f * vs_all * dy * dy;
-          v[0] = vs_cd * (r0.z * dx + r0.w * dy);
-          v[1] = vs_cd * (r0.w * dx + r1.x * dy);
+          // d sigma / d mean2d = (A dx + B dy, B dx + C dy) with A = -2 ln2 a', B = -ln2 b', C = -2 ln2 c'
+          const float k = -DNR_LN2 * vs_cd;
+          v[0] = k * (2.0f * q0.z * dx + q0.w * dy);
+          v[1] = k * (q0.w * dx + 2.0f * q1.x * dy);
           v[2] = fabsf(v[0]);
           v[3] = fabsf(v[1]);
           v[7] = vis * v_alpha_all;

@@ -135,6 +135,11 @@ class DNSplatterModelConfig:
     reset_alpha_every: int = 30
     resolution_schedule: int = 3000
     cull_alpha_thresh: float = 0.1
+    # ---- dn_splatter_b200 options (not in the reference) ----
+    exact_isect_lists: bool = False
+    """Emit gsplat's full bbox tile lists instead of the precise-hit lists (parity debugging; images are identical)."""
+    sync_free: bool = False
+    """Size intersection buffers from earlier views instead of reading the count back (no host sync per view)."""
 
     def setup(self, **kwargs):
         return self._target(self, **kwargs)
@@ -375,6 +380,7 @@ class DNSplatterModel(torch.nn.Module):
             background=background, render_normals=cfg.predict_normals,
             c2w=camera.camera_to_worlds.reshape(-1, 3, 4)[0].detach().to(dev),
             grad_sink=self._bucket.sink() if (self._bucket is not None and torch.is_grad_enabled()) else None,
+            exact_lists=cfg.exact_isect_lists, sync_free=cfg.sync_free,
         )
         self.raster_out = out
         self.xys = out.means2d[None]  # [1,N,2]; .grad / .absgrad live on out.means2d after backward

@@ -23,6 +23,68 @@ from . import _lib as L
 
 TILE = 16
 
+
+class _CapacityTracker:
+    """Sync-free sizing of the intersection buffers: the count of every view is copied to pinned host memory
+    asynchronously; capacity for the next view = 1.3 x the largest count seen so far (rounded up).  A view whose
+    count exceeded its capacity was rendered without its farthest intersections; `overflows` counts those."""
+
+    SLOTS = 256
+
+    def __init__(self):
+        self.max_seen, self.overflows, self.pending, self.seeds = 0, 0, [], 0
+        self.host, self.slot = None, 0
+
+    def seed(self, count: int):
+        self.max_seen = max(self.max_seen, count)
+        self.seeds += 1
+
+    def ready(self) -> bool:
+        self.drain()
+        return self.seeds >= 2
+
+    def capacity(self) -> int:
+        return int(self.max_seen * 1.3) + 4096
+
+    def observe(self, n_isects_dev: Tensor, cap: int):
+        if self.host is None:
+            self.host = torch.zeros(self.SLOTS, dtype=torch.int64).pin_memory()
+        if len(self.pending) >= self.SLOTS - 1:
+            self.drain(wait=True)
+        host = self.host[self.slot:self.slot + 1]
+        self.slot = (self.slot + 1) % self.SLOTS
+        host.copy_(n_isects_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending.append((host, ev, cap))
+
+    def drain(self, wait: bool = False):
+        keep = []
+        for host, ev, cap in self.pending:
+            if wait:
+                ev.synchronize()
+            if ev.query():
+                c = int(host.item())
+                self.max_seen = max(self.max_seen, c)
+                if c > cap:
+                    self.overflows += 1
+            else:
+                keep.append((host, ev, cap))
+        self.pending = keep
+
+
+_CAPACITY: dict = {}
+
+
+def capacity_report() -> dict:
+    """{key: (max intersections seen, truncated views)} for the sync-free mode; waits for pending counts."""
+    out = {}
+    for k, t in _CAPACITY.items():
+        t.drain(wait=True)
+        out[k] = (t.max_seen, t.overflows)
+    return out
+
+
 # Optional per-stage device timing (bench.py's roofline pass): when STAGE_EVENTS is a list, every C-ABI
 # stage call is bracketed by CUDA events on the launching stream and (name, start, end) is appended.
 STAGE_EVENTS = None
@@ -52,6 +114,8 @@ class RasterSettings:
     activated: bool = False  # inputs already exp()/sigmoid()-activated (gsplat's own signature)
     background: Tuple[float, float, float] = (0.0, 0.0, 0.0)
     surface_normal: bool = True
+    exact_lists: bool = False  # parity mode: gsplat's full bbox intersection lists instead of the precise-hit lists
+    sync_free: bool = False  # size the intersection buffers from past views instead of reading the count back
 
 
 class RasterOutput(NamedTuple):
@@ -100,6 +164,8 @@ def _base_args(s: RasterSettings, n: int, sh_bases: int, accumulate: bool = Fals
         flags |= L.FLAG_NORMALS
     if accumulate:
         flags |= L.FLAG_ACCUMULATE
+    if s.exact_lists:
+        flags |= L.FLAG_EXACT_LISTS
     a.flags = flags
     a.near_plane, a.far_plane, a.eps2d, a.radius_clip = s.near_plane, s.far_plane, s.eps2d, 0.0
     a.background[0], a.background[1], a.background[2] = s.background
@@ -148,20 +214,32 @@ class _DnRasterize(torch.autograd.Function):
         tiles_per_gauss = torch.empty(n, **i32)
         depth_keys = torch.empty(n, **i32)
         records = torch.empty(n, rec_f, **f32)
+        cull_lim = torch.empty(n, **f32)
+        n_isects_dev = torch.empty(1, dtype=torch.int64, device=dev)
 
         a = _base_args(s, n, sh_bases)
         _set(a, viewmat=viewmat, K=K, c2w=c2w, means=means, quats=quats, scales=scales, opacities=opac, sh_dc=sh_dc,
              sh_rest=sh_rest if sh_bases > 1 else None, radii=radii, means2d=means2d, depths=depths, conics=conics,
              opac_act=opac_act, compensations=comp, colors=colors,
              normals_world=normals_world if s.render_normals else None, tiles_per_gauss=tiles_per_gauss,
-             depth_keys=depth_keys, records=records)
+             depth_keys=depth_keys, records=records, cull_lim=cull_lim, n_isects_dev=n_isects_dev)
         L.check(_timed("project_fwd", lib.dnr_project_fwd, C.byref(a), st), "dnr_project_fwd")
 
         ws_scan = torch.empty(lib.dnr_bin_scan_workspace_bytes(n), dtype=torch.uint8, device=dev)
         _set(a, ws_scan=ws_scan)
-        total = C.c_int64(0)
-        L.check(_timed("bin_scan", lib.dnr_bin_scan, C.byref(a), st, C.byref(total)), "dnr_bin_scan")
-        n_isects = int(total.value)
+        cap_key = (dev.index, n, W, H, s.render_normals, s.exact_lists)
+        tracker = _CAPACITY.get(cap_key) if s.sync_free else None
+        if tracker is not None and tracker.ready():
+            # sync-free: nothing is read back on this stream; capacity comes from the counts of earlier views
+            L.check(_timed("bin_scan", lib.dnr_bin_scan, C.byref(a), st, None), "dnr_bin_scan")
+            n_isects = tracker.capacity()
+            tracker.observe(n_isects_dev, n_isects)
+        else:
+            total = C.c_int64(0)
+            L.check(_timed("bin_scan", lib.dnr_bin_scan, C.byref(a), st, C.byref(total)), "dnr_bin_scan")
+            n_isects = int(total.value)
+            if s.sync_free:
+                _CAPACITY.setdefault(cap_key, _CapacityTracker()).seed(n_isects)
         a.n_isects = n_isects
         ws_sort = torch.empty(lib.dnr_bin_sort_workspace_bytes(n, n_isects, n_tiles), dtype=torch.uint8, device=dev)
         flatten_ids = torch.empty(max(n_isects, 1), **i32)
@@ -193,6 +271,7 @@ class _DnRasterize(torch.autograd.Function):
         normal_ret = out_normal if s.render_normals else torch.zeros(H, W, 3, **f32)
         sn_ret = out_sn if s.surface_normal else torch.zeros(H, W, 3, **f32)
         info = dict(flatten_ids=flatten_ids[:n_isects], tile_offsets=tile_offsets, last_ids=last_ids, n_isects=n_isects,
+                    n_isects_dev=n_isects_dev,
                     colors=colors, opacities=opac_act, compensations=comp, tile_width=tiles_x, tile_height=tiles_y,
                     depth_max=depth_max)
         ctx.grad_sink = holder.pop("grad_sink", None)
@@ -258,6 +337,7 @@ def dn_rasterize(
     far_plane: float = 1e10, eps2d: float = 0.3, antialiased: bool = False,
     background: Sequence[float] = (0.0, 0.0, 0.0), render_normals: bool = True, c2w: Optional[Tensor] = None,
     activated: bool = False, surface_normal: bool = True, grad_sink: Optional[dict] = None,
+    exact_lists: bool = False, sync_free: bool = False,
 ) -> RasterOutput:
     """Renders one view.  Inputs are the reference's RAW gauss_params (log-scales, opacity logits,
     un-normalised wxyz quats, SH coefficients split as features_dc / features_rest) unless
@@ -268,7 +348,8 @@ def dn_rasterize(
     bg = tuple(float(b) for b in background)
     settings = RasterSettings(width=int(width), height=int(height), sh_degree=int(sh_degree), near_plane=near_plane,
                               far_plane=far_plane, eps2d=eps2d, antialiased=antialiased, render_normals=render_normals,
-                              activated=activated, background=bg, surface_normal=surface_normal)
+                              activated=activated, background=bg, surface_normal=surface_normal, exact_lists=exact_lists,
+                              sync_free=sync_free)
     info: dict = {}
     if grad_sink is not None:
         # dict with fp32 contiguous buffers shaped like the six parameters (keys: means, quats, scales, opacities,

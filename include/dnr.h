@@ -49,6 +49,7 @@ extern "C" {
 #define DNR_FLAG_ANTIALIASED 2u /* rasterize_mode == "antialiased": opacity *= compensation */
 #define DNR_FLAG_NORMALS 4u     /* predict_normals: render the per-Gaussian normal channels */
 #define DNR_FLAG_ACCUMULATE 8u  /* project_bwd adds into the parameter-gradient buffers */
+#define DNR_FLAG_EXACT_LISTS 16u /* parity mode: emit gsplat's full bbox intersection lists (no precise-hit cull) */
 
 /* floats per packed per-Gaussian raster record, without / with normals */
 #define DNR_REC_FLOATS 12
@@ -68,7 +69,8 @@ typedef struct DnrArgs {
   float near_plane, far_plane, eps2d, radius_clip;
   float background[3];
   float reserved1;
-  int64_t n_isects; /* I: filled by the caller from dnr_bin_scan's result */
+  int64_t n_isects; /* capacity of flatten_ids / ws_sort in intersections (>= the count dnr_bin_scan reports, or an
+                       estimate when running sync-free: see n_isects_dev) */
 
   /* ---- camera (device) ---- */
   const float* viewmat; /* [4,4] */
@@ -95,12 +97,15 @@ typedef struct DnrArgs {
   int32_t* tiles_per_gauss; /* [N] */
   uint32_t* depth_keys;     /* [N] bit pattern of depth, 0xFFFFFFFF when culled */
   float* records;           /* [N, DNR_REC_FLOATS(_N)] packed raster records */
+  float* cull_lim;          /* [N] ln(255 * sigmoid opacity) + margin: largest sigma that can still reach alpha >= 1/255 */
 
   /* ---- binning ---- */
   void* ws_scan;         /* dnr_bin_scan_workspace_bytes(N) */
   void* ws_sort;         /* dnr_bin_sort_workspace_bytes(N, I, n_tiles) */
   int32_t* flatten_ids;  /* [I] Gaussian ids sorted by (tile, depth, id) */
   int32_t* tile_offsets; /* [n_tiles+1] */
+  int64_t* n_isects_dev; /* [1] device copy of the intersection count (may exceed the capacity: then the render is
+                            truncated and the caller must retry with a larger n_isects) */
 
   /* ---- raster forward outputs / backward state ---- */
   float* out_rgb;      /* [H,W,3] clamp(C + (1-alpha) bg, 0, 1) */
@@ -147,8 +152,10 @@ const char* dnr_error_string(int code);
 int dnr_project_fwd(const DnrArgs* a, void* stream);
 
 size_t dnr_bin_scan_workspace_bytes(int32_t n_gauss);
-/* Sorts visible Gaussians by depth, scans their tile counts, copies the total to *n_isects_host and
- * synchronises the stream (the one documented host sync). */
+/* Sorts visible Gaussians by depth, counts the tiles each one really touches (or its whole bbox with
+ * DNR_FLAG_EXACT_LISTS), scans the counts and stores the total in *a->n_isects_dev.  If n_isects_host is not
+ * NULL the total is also copied there and the stream is synchronised (the one documented host sync);
+ * pass NULL to stay asynchronous and size by capacity. */
 int dnr_bin_scan(const DnrArgs* a, void* stream, int64_t* n_isects_host);
 size_t dnr_bin_sort_workspace_bytes(int32_t n_gauss, int64_t n_isects, int32_t n_tiles);
 int dnr_bin_sort(const DnrArgs* a, void* stream);

@@ -45,7 +45,7 @@ def test_projection_and_binning_bit_exact(case):
     proj = G.project_gaussians(act["means"], act["quats"], act["scales"], vm, K, W, H)
     tpg, isect_ids, flat, offs, _ = G.isect_tiles(proj["means2d"], proj["radii"], proj["depths"], 16, W, H)
 
-    _, out = cuda_outputs(act, cam, activated=True, viewmat=vm)
+    _, out = cuda_outputs(act, cam, activated=True, viewmat=vm, exact_lists=True)
     assert torch.equal(out.radii.cpu(), proj["radii"]), "radii must be bit-exact"
     assert torch.equal(out.tiles_per_gauss.cpu(), tpg), "tiles_per_gauss must be bit-exact"
     for name, got, want in (("means2d", out.means2d, proj["means2d"]), ("depths", out.depths, proj["depths"]),
@@ -68,7 +68,7 @@ def test_projection_and_binning_bit_exact(case):
 def test_forward_images_match_oracle(case, normals):
     params, cam = scene_and_camera(**case)
     _, ref = oracle_outputs(params, cam, predict_normals=normals)
-    _, out = cuda_outputs(params, cam, render_normals=normals)
+    _, out = cuda_outputs(params, cam, render_normals=normals, exact_lists=True)  # last_ids index gsplat's full lists
     # raw-parameter path: expf on the GPU vs torch.exp on the CPU may move a radius across an integer
     mism = (out.radii.cpu() != ref["info"]["radii"]).float().mean().item()
     assert mism <= 2e-3, f"radii mismatch fraction {mism}"
@@ -141,3 +141,45 @@ def test_all_culled_and_single_gaussian():
     _, out = cuda_outputs(one, cam)
     frac, mx = frac_close(out.rgb, ref["rgb"], atol=1e-4)
     assert frac >= 0.999, (frac, mx)
+
+
+@needs_cuda
+@pytest.mark.parametrize("case", CASES + [dict(n=20000, width=320, height=240, view=2)])
+def test_precise_hit_lists_render_bit_identical_images(case):
+    """The default emission drops (tile, Gaussian) pairs that no pixel of the tile can reach; that must not change
+    a single bit of any output, and the kept list must be an order-preserving sub-list of gsplat's."""
+    params, cam = scene_and_camera(**case)
+    _, full = cuda_outputs(params, cam, exact_lists=True)
+    _, cut = cuda_outputs(params, cam)
+    for name in ("rgb", "depth", "normal", "alpha", "surface_normal"):
+        assert torch.equal(getattr(full, name), getattr(cut, name)), f"{name} differs between exact and precise-hit lists"
+    assert torch.equal(full.tiles_per_gauss, cut.tiles_per_gauss)  # API output stays gsplat's bbox count
+    assert cut.info["n_isects"] < full.info["n_isects"]
+    fo, co = full.info["tile_offsets"].cpu().tolist(), cut.info["tile_offsets"].cpu().tolist()
+    ff, cf = full.info["flatten_ids"].cpu().tolist(), cut.info["flatten_ids"].cpu().tolist()
+    for t in range(len(fo) - 1):
+        it = iter(ff[fo[t]:fo[t + 1]])
+        assert all(g in it for g in cf[co[t]:co[t + 1]]), f"tile {t}: kept list is not a sub-sequence"
+
+
+@needs_cuda
+def test_sync_free_capacity_mode_matches_sync_mode():
+    import dn_splatter_b200.rasterize as R
+
+    params, cam = scene_and_camera(5000, 256, 192, view=1)
+    _, ref = cuda_outputs(params, cam)
+    outs = [cuda_outputs(params, cam, sync_free=True)[1] for _ in range(4)]  # 2 seeding views, then sync-free
+    for o in outs:
+        for name in ("rgb", "depth", "normal", "alpha"):
+            assert torch.equal(getattr(o, name), getattr(ref, name))
+    assert int(outs[-1].info["n_isects_dev"]) == ref.info["n_isects"]
+    assert outs[-1].info["n_isects"] >= ref.info["n_isects"]  # capacity, not count
+    rep = R.capacity_report()
+    assert all(over == 0 for _, over in rep.values())
+    # backward through a capacity-sized list
+    p, o = cuda_outputs(params, cam, requires_grad=True, sync_free=True)
+    pr, r = cuda_outputs(params, cam, requires_grad=True)
+    _loss(o.rgb, o.depth, o.normal, o.alpha).backward()
+    _loss(r.rgb, r.depth, r.normal, r.alpha).backward()
+    for k in p:
+        torch.testing.assert_close(p[k].grad, pr[k].grad, rtol=1e-4, atol=1e-6)

@@ -65,6 +65,13 @@ ScanWs carve_scan(void* base, int32_t n) {
   return w;
 }
 
+// the padding key has all bits set: sort one bit more than the tile ids need so it lands behind every tile
+template <typename KeyT>
+inline int sort_end_bit(int tile_bits) {
+  const int full = (int)(8 * sizeof(KeyT));
+  return tile_bits + 1 < full ? tile_bits + 1 : full;
+}
+
 template <typename KeyT>
 struct SortWs {
   KeyT* keys_in;
@@ -86,7 +93,7 @@ SortWs<KeyT> carve_sort(void* base, int64_t n_isects, int tile_bits) {
   w.gids_in = (int32_t*)(p + off); off += align_up(n * 4);
   size_t sort_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const KeyT*)nullptr, (KeyT*)nullptr, (const int32_t*)nullptr,
-                                  (int32_t*)nullptr, (int64_t)n, 0, tile_bits);
+                                  (int32_t*)nullptr, (int64_t)n, 0, sort_end_bit<KeyT>(tile_bits));
   w.cub_bytes = sort_bytes;
   w.cub_temp = (void*)(p + off); off += align_up(sort_bytes);
   w.total = off;
@@ -213,8 +220,7 @@ int bin_sort_impl(const DnrArgs* a, cudaStream_t s, int n_tiles, int tile_bits) 
     pad_kernel<KeyT><<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(w.keys_in, w.gids_in, a->n_isects_dev, cap);
     DNR_CHECK_LAUNCH();
     size_t bytes = w.cub_bytes;
-    // the padding key has all bits set: sort one bit more than the tile ids need so it lands behind every tile
-    const int end_bit = min(tile_bits + 1, (int)(8 * sizeof(KeyT)));
+    const int end_bit = sort_end_bit<KeyT>(tile_bits);
     DNR_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, bytes, (const KeyT*)w.keys_in, w.keys_out,
                                              (const int32_t*)w.gids_in, a->flatten_ids, cap, 0, end_bit, s));
   }

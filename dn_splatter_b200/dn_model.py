@@ -20,7 +20,7 @@ from torch import Tensor
 
 from .cameras import Cameras, is_camera
 from .losses import DepthLoss, DepthLossType, TVLoss
-from .rasterize import dn_rasterize, get_viewmat
+from .rasterize import dn_rasterize, get_viewmat, to_device_async
 from .regularization_strategy import AGSMeshRegularization, DNRegularization
 from .utils.normal_utils import normal_from_depth_image
 
@@ -365,10 +365,16 @@ class DNSplatterModel(torch.nn.Module):
         scale_fac = self._get_downscale_factor()
         camera.rescale_output_resolution(1 / scale_fac)
         dev = self.device
-        c2w = c2w_opt.reshape(-1, 3, 4)[0].to(dev)
+        # per-camera device constants are cached on the camera object: the step itself issues no H2D copy
+        cache = camera.__dict__.setdefault("_dnr_cache", {})
+        key = (str(dev), scale_fac)
+        if key not in cache:
+            cache[key] = (to_device_async(camera.get_intrinsics_matrices()[0].float().cpu(), dev),
+                          int(camera.width.flatten()[0]), int(camera.height.flatten()[0]),
+                          to_device_async(camera.camera_to_worlds.reshape(-1, 3, 4)[0].detach().float(), dev))
+        K, W, H, c2w_fixed = cache[key]
+        c2w = to_device_async(c2w_opt.reshape(-1, 3, 4)[0], dev)
         viewmat = get_viewmat(c2w)
-        K = camera.get_intrinsics_matrices()[0].to(dev)
-        W, H = int(camera.width.flatten()[0]), int(camera.height.flatten()[0])
         self.last_size = (H, W)
         camera.rescale_output_resolution(scale_fac)
         sh_degree_to_use = min(self.step // cfg.sh_degree_interval, cfg.sh_degree)
@@ -378,7 +384,7 @@ class DNSplatterModel(torch.nn.Module):
             self.means, self.quats, self.scales, self.opacities, self.features_dc, self.features_rest, viewmat, K, W, H,
             sh_degree=sh_degree_to_use, near_plane=0.01, far_plane=1e10, antialiased=cfg.rasterize_mode == "antialiased",
             background=background, render_normals=cfg.predict_normals,
-            c2w=camera.camera_to_worlds.reshape(-1, 3, 4)[0].detach().to(dev),
+            c2w=c2w_fixed,
             grad_sink=self._bucket.sink() if (self._bucket is not None and torch.is_grad_enabled()) else None,
             exact_lists=cfg.exact_isect_lists, sync_free=cfg.sync_free,
         )
@@ -399,8 +405,17 @@ class DNSplatterModel(torch.nn.Module):
         self.camera = camera
         return {
             "rgb": out.rgb, "depth": out.depth, "normal": normals_im, "surface_normal": out.surface_normal,
-            "accumulation": out.alpha, "background": background.to(dev),
+            "accumulation": out.alpha, "background": self._background_on_device(background, dev),
         }
+
+    def _background_on_device(self, background: Tensor, dev) -> Tensor:
+        if background is self.background_color:  # fixed colour: upload once
+            cached = self.__dict__.get("_bg_dev")
+            if cached is None or cached.device != torch.device(dev):
+                cached = to_device_async(background, dev)
+                self.__dict__["_bg_dev"] = cached
+            return cached
+        return to_device_async(background, dev)
 
     def forward(self, camera):
         return self.get_outputs(camera)
@@ -426,10 +441,10 @@ class DNSplatterModel(torch.nn.Module):
             main = main + cfg.ssim_lambda * (1 - ssim(gt_img.permute(2, 0, 1)[None], pred_img.permute(2, 0, 1)[None]))
         if cfg.use_scale_regularization and self.step % 10 == 0:
             se = torch.exp(self.scales)
-            reg = torch.maximum(se.amax(dim=-1) / se.amin(dim=-1), torch.tensor(cfg.max_gauss_ratio, device=se.device)) - cfg.max_gauss_ratio
+            reg = torch.clamp(se.amax(dim=-1) / se.amin(dim=-1), min=cfg.max_gauss_ratio) - cfg.max_gauss_ratio
             scale_reg = 0.1 * reg.mean()
         else:
-            scale_reg = torch.tensor(0.0, device=self.device)
+            scale_reg = torch.zeros((), device=self.device)
         return {"main_loss": main, "scale_reg": scale_reg}
 
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
@@ -467,7 +482,7 @@ class DNSplatterModel(torch.nn.Module):
                 cx=float(cam.cx.flatten()[0]), cy=float(cam.cy.flatten()[0]),
                 img_size=(int(cam.width.flatten()[0]), int(cam.height.flatten()[0])),
                 c2w=torch.eye(4, dtype=torch.float, device=depth_out.device), device=self.device, smooth=False)
-            gt_normal = (1 + gt_normal * torch.tensor([1.0, -1.0, -1.0], device=depth_out.device)) / 2
+            gt_normal = (1 + torch.cat([gt_normal[..., :1], -gt_normal[..., 1:]], dim=-1)) / 2
         else:
             gt_normal = None
         depth_gt = sensor_depth_gt

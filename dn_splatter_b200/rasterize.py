@@ -360,12 +360,20 @@ def dn_rasterize(
 
 
 def get_viewmat(c2w: Tensor) -> Tensor:
-    """nerfstudio `get_viewmat` [EXT]: OpenGL camera_to_world [..,3,4] -> OpenCV world->camera [4,4]."""
+    """nerfstudio `get_viewmat` [EXT]: OpenGL camera_to_world [..,3,4] -> OpenCV world->camera [4,4].
+    Device-only ops (no host constants): building it must not trigger a blocking H2D copy."""
     c2w = c2w.reshape(3, 4)
-    R = c2w[:, :3] * torch.tensor([1.0, -1.0, -1.0], dtype=c2w.dtype, device=c2w.device)
-    Rinv = R.T
-    vm = torch.zeros(4, 4, dtype=c2w.dtype, device=c2w.device)
-    vm[:3, :3] = Rinv
-    vm[:3, 3] = -(Rinv @ c2w[:, 3])
-    vm[3, 3] = 1.0
-    return vm
+    Rinv = torch.cat([c2w[:, :1], -c2w[:, 1:3]], dim=1).T  # (R * diag(1,-1,-1))^T
+    t = -(Rinv @ c2w[:, 3:4])
+    bottom = torch.zeros(1, 4, dtype=c2w.dtype, device=c2w.device)
+    bottom[0, 3] = 1.0
+    return torch.cat([torch.cat([Rinv, t], dim=1), bottom], dim=0)
+
+
+def to_device_async(t: Tensor, device) -> Tensor:
+    """Small host tensor -> device without blocking the host (pinned staging + non_blocking copy)."""
+    if t.device == torch.device(device):
+        return t
+    if t.device.type == "cpu" and torch.device(device).type == "cuda":
+        return t.pin_memory().to(device, non_blocking=True)
+    return t.to(device)

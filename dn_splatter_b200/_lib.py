@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdnr_b200.so")
 
 FLAG_ACTIVATED, FLAG_ANTIALIASED, FLAG_NORMALS, FLAG_ACCUMULATE, FLAG_EXACT_LISTS = 1, 2, 4, 8, 16
+FLAG_HOST_CAMERA = 32
 REC_FLOATS, REC_FLOATS_N, GRAD_FLOATS = 12, 16, 16
 DEPTH_LOSS_TYPES = {None: 0, "EdgeAwareLogL1": 1, "LogL1": 2, "L1": 3, "MSE": 4}
 
@@ -37,6 +38,7 @@ class DnrArgs(C.Structure):
         ("v_means2d", _p), ("v_means2d_abs", _p),
         ("gt_depth", _p), ("gt_normal", _p), ("gt_rgb", _p), ("loss_partials", _p), ("v_loss", _p),
         ("depth_lambda", _f), ("depth_tolerance", _f), ("depth_loss_type", _i), ("use_normal_loss", _i),
+        ("host_cam", _f * 32),
     ]
 
 

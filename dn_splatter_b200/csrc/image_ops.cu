@@ -13,9 +13,13 @@ namespace {
 
 struct Intr { float fx, fy, cx, cy; };
 
-__device__ __forceinline__ Intr load_intr(const float* K) {
+__device__ __forceinline__ Intr load_intr(const DnrArgs& a) {
   Intr k;
-  k.fx = __ldg(K + 0); k.fy = __ldg(K + 4); k.cx = __ldg(K + 2); k.cy = __ldg(K + 5);
+  if (a.flags & DNR_FLAG_HOST_CAMERA) {
+    k.fx = a.host_cam[16]; k.fy = a.host_cam[17]; k.cx = a.host_cam[18]; k.cy = a.host_cam[19];
+  } else {
+    k.fx = __ldg(a.K + 0); k.fy = __ldg(a.K + 4); k.cx = __ldg(a.K + 2); k.cy = __ldg(a.K + 5);
+  }
   return k;
 }
 
@@ -57,7 +61,7 @@ __global__ void __launch_bounds__(256) finalize_fwd_kernel(const DnrArgs a) {
   if (a.out_surface_normal) {
     float n[3] = {0.f, 0.f, 0.f};
     if (i > 0 && j > 0 && i < H - 1 && j < W - 1) {
-      const Intr k = load_intr(a.K);
+      const Intr k = load_intr(a);
       stencil_normal(k, i, j, depth_at, n);
     }
     // flip y,z (dn_model.py:600-602) and map to [0,1] (:603); border stays exactly 0.5
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(256) normal_from_depth_kernel(const DnrArgs a)
   auto depth_at = [&](int y, int x) -> float { return a.out_depth[y * W + x]; };
   float n[3] = {0.f, 0.f, 0.f};
   if (i > 0 && j > 0 && i < H - 1 && j < W - 1) {
-    const Intr k = load_intr(a.K);
+    const Intr k = load_intr(a);
     stencil_normal(k, i, j, depth_at, n);
   }
   const int pix = i * W + j;
@@ -241,7 +245,7 @@ extern "C" int dnr_finalize_fwd(const DnrArgs* a, void* stream) {
   if (!a) return DNR_E_NULL;
   if (a->width <= 0 || a->height <= 0) return DNR_E_SIZE;
   if (!a->out_depth || !a->out_alpha || !a->depth_max) return DNR_E_NULL;
-  if (a->out_surface_normal && !a->K) return DNR_E_NULL;
+  if (a->out_surface_normal && !a->K && !(a->flags & DNR_FLAG_HOST_CAMERA)) return DNR_E_NULL;
   finalize_fwd_kernel<<<img_grid(a), 256, 0, (cudaStream_t)stream>>>(*a);
   DNR_CHECK_LAUNCH();
   return 0;
@@ -250,7 +254,8 @@ extern "C" int dnr_finalize_fwd(const DnrArgs* a, void* stream) {
 extern "C" int dnr_normal_from_depth(const DnrArgs* a, void* stream) {
   if (!a) return DNR_E_NULL;
   if (a->width <= 0 || a->height <= 0) return DNR_E_SIZE;
-  if (!a->out_depth || !a->out_surface_normal || !a->K) return DNR_E_NULL;
+  if (!a->out_depth || !a->out_surface_normal) return DNR_E_NULL;
+  if (!a->K && !(a->flags & DNR_FLAG_HOST_CAMERA)) return DNR_E_NULL;
   normal_from_depth_kernel<<<img_grid(a), 256, 0, (cudaStream_t)stream>>>(*a);
   DNR_CHECK_LAUNCH();
   return 0;

@@ -21,24 +21,25 @@ struct Cam {
 };
 
 __device__ __forceinline__ void load_cam(const DnrArgs& a, Cam& c) {
+  const bool host = (a.flags & DNR_FLAG_HOST_CAMERA) != 0;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) c.W[i][j] = __ldg(a.viewmat + i * 4 + j);
-    c.t[i] = __ldg(a.viewmat + i * 4 + 3);
+    for (int j = 0; j < 3; ++j) c.W[i][j] = host ? a.host_cam[i * 4 + j] : __ldg(a.viewmat + i * 4 + j);
+    c.t[i] = host ? a.host_cam[i * 4 + 3] : __ldg(a.viewmat + i * 4 + 3);
   }
-  c.fx = __ldg(a.K + 0);
-  c.fy = __ldg(a.K + 4);
-  c.cx = __ldg(a.K + 2);
-  c.cy = __ldg(a.K + 5);
+  c.fx = host ? a.host_cam[16] : __ldg(a.K + 0);
+  c.fy = host ? a.host_cam[17] : __ldg(a.K + 4);
+  c.cx = host ? a.host_cam[18] : __ldg(a.K + 2);
+  c.cy = host ? a.host_cam[19] : __ldg(a.K + 5);
 #pragma unroll
   for (int j = 0; j < 3; ++j) c.campos[j] = -((c.W[0][j] * c.t[0] + c.W[1][j] * c.t[1]) + c.W[2][j] * c.t[2]);
-  if (a.c2w != nullptr) {
+  if (host || a.c2w != nullptr) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) c.c2wR[i][j] = __ldg(a.c2w + i * 4 + j);
-      c.c2wT[i] = __ldg(a.c2w + i * 4 + 3);
+      for (int j = 0; j < 3; ++j) c.c2wR[i][j] = host ? a.host_cam[20 + i * 4 + j] : __ldg(a.c2w + i * 4 + j);
+      c.c2wT[i] = host ? a.host_cam[20 + i * 4 + 3] : __ldg(a.c2w + i * 4 + 3);
     }
   }
 }
@@ -570,13 +571,15 @@ extern "C" int dnr_project_fwd(const DnrArgs* a, void* stream) {
   if (a->n_gauss <= 0 || a->width <= 0 || a->height <= 0) return DNR_E_SIZE;
   if (a->tile_size != DNR_TILE || a->sh_degree < 0 || a->sh_degree > 3 || (a->sh_degree + 1) * (a->sh_degree + 1) > a->sh_bases)
     return DNR_E_OPTION;
-  if (!a->viewmat || !a->K || !a->means || !a->quats || !a->scales || !a->opacities || !a->sh_dc || !a->radii ||
+  const bool hostcam = (a->flags & DNR_FLAG_HOST_CAMERA) != 0;
+  if (!hostcam && (!a->viewmat || !a->K)) return DNR_E_NULL;
+  if (!a->means || !a->quats || !a->scales || !a->opacities || !a->sh_dc || !a->radii ||
       !a->means2d || !a->depths || !a->conics || !a->opac_act || !a->colors || !a->tiles_per_gauss || !a->depth_keys ||
       !a->records)
     return DNR_E_NULL;
   if (a->sh_bases > 1 && !a->sh_rest) return DNR_E_NULL;
   const bool normals = (a->flags & DNR_FLAG_NORMALS) != 0;
-  if (normals && !a->c2w) return DNR_E_NULL;
+  if (normals && !hostcam && !a->c2w) return DNR_E_NULL;
   const int block = 256, grid = (a->n_gauss + block - 1) / block;
   cudaStream_t s = (cudaStream_t)stream;
   if (normals) project_fwd_kernel<true><<<grid, block, 0, s>>>(*a);
@@ -588,12 +591,14 @@ extern "C" int dnr_project_fwd(const DnrArgs* a, void* stream) {
 extern "C" int dnr_project_bwd(const DnrArgs* a, void* stream) {
   if (!a) return DNR_E_NULL;
   if (a->n_gauss <= 0) return DNR_E_SIZE;
-  if (!a->viewmat || !a->K || !a->means || !a->quats || !a->scales || !a->opacities || !a->sh_dc || !a->radii ||
+  const bool hostcam = (a->flags & DNR_FLAG_HOST_CAMERA) != 0;
+  if (!hostcam && (!a->viewmat || !a->K)) return DNR_E_NULL;
+  if (!a->means || !a->quats || !a->scales || !a->opacities || !a->sh_dc || !a->radii ||
       !a->grad_records || !a->v_means || !a->v_quats || !a->v_scales || !a->v_opacities || !a->v_sh_dc)
     return DNR_E_NULL;
   if (a->sh_bases > 1 && (!a->sh_rest || !a->v_sh_rest)) return DNR_E_NULL;
   const bool normals = (a->flags & DNR_FLAG_NORMALS) != 0;
-  if (normals && !a->c2w) return DNR_E_NULL;
+  if (normals && !hostcam && !a->c2w) return DNR_E_NULL;
   const int block = 256, grid = (a->n_gauss + block - 1) / block;
   cudaStream_t s = (cudaStream_t)stream;
   if (normals) project_bwd_kernel<true><<<grid, block, 0, s>>>(*a);

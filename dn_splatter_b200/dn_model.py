@@ -365,16 +365,14 @@ class DNSplatterModel(torch.nn.Module):
         scale_fac = self._get_downscale_factor()
         camera.rescale_output_resolution(1 / scale_fac)
         dev = self.device
-        # per-camera device constants are cached on the camera object: the step itself issues no H2D copy
+        # Per-camera constants are cached on the camera object as HOST tensors and handed to the kernels by value:
+        # the step issues no H2D copy and no device op for the camera (camera optimisation is off on this path).
         cache = camera.__dict__.setdefault("_dnr_cache", {})
-        key = (str(dev), scale_fac)
-        if key not in cache:
-            cache[key] = (to_device_async(camera.get_intrinsics_matrices()[0].float().cpu(), dev),
-                          int(camera.width.flatten()[0]), int(camera.height.flatten()[0]),
-                          to_device_async(camera.camera_to_worlds.reshape(-1, 3, 4)[0].detach().float(), dev))
-        K, W, H, c2w_fixed = cache[key]
-        c2w = to_device_async(c2w_opt.reshape(-1, 3, 4)[0], dev)
-        viewmat = get_viewmat(c2w)
+        if scale_fac not in cache:
+            c2w_host = camera.camera_to_worlds.reshape(-1, 3, 4)[0].detach().float().cpu()
+            cache[scale_fac] = (camera.get_intrinsics_matrices()[0].float().cpu(), int(camera.width.flatten()[0]),
+                                int(camera.height.flatten()[0]), c2w_host, get_viewmat(c2w_host))
+        K, W, H, c2w_fixed, viewmat = cache[scale_fac]
         self.last_size = (H, W)
         camera.rescale_output_resolution(scale_fac)
         sh_degree_to_use = min(self.step // cfg.sh_degree_interval, cfg.sh_degree)

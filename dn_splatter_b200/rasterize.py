@@ -172,6 +172,12 @@ def _base_args(s: RasterSettings, n: int, sh_bases: int, accumulate: bool = Fals
     return a
 
 
+def _set_host_cam(a: L.DnrArgs, host_cam) -> None:
+    if host_cam is not None:
+        a.flags |= L.FLAG_HOST_CAMERA
+        a.host_cam[:] = host_cam
+
+
 def _set(a: L.DnrArgs, **tensors: Optional[Tensor]) -> None:
     for k, t in tensors.items():
         setattr(a, k, _ptr(t))
@@ -182,13 +188,25 @@ class _DnRasterize(torch.autograd.Function):
     def forward(ctx, means, quats, scales, opacities, sh_dc, sh_rest, viewmat, K, c2w, settings: RasterSettings, holder: dict):
         lib = L.load()
         s = settings
-        dev = _require_cuda(means, quats, scales, opacities, sh_dc, sh_rest, viewmat, K)
+        dev = _require_cuda(means, quats, scales, opacities, sh_dc, sh_rest)
+        # camera on the host (CPU tensors) -> passed by value, no device traffic; on the device -> read by the kernels
+        host_cam = None
+        if viewmat.device.type == "cpu":
+            host_cam = viewmat.detach().float().reshape(16).tolist()
+            Kc = K.detach().float().cpu().reshape(3, 3)
+            host_cam += [float(Kc[0, 0]), float(Kc[1, 1]), float(Kc[0, 2]), float(Kc[1, 2])]
+            host_cam += c2w.detach().float().cpu().reshape(12).tolist() if c2w is not None else [0.0] * 12
+        else:
+            _require_cuda(means, viewmat, K)
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         means, quats, scales = means.contiguous().float(), quats.contiguous().float(), scales.contiguous().float()
         opac = opacities.contiguous().float().view(-1)
         sh_dc, sh_rest = sh_dc.contiguous().float(), sh_rest.contiguous().float()
-        viewmat, K = viewmat.contiguous().float().view(4, 4), K.contiguous().float().view(3, 3)
+        if host_cam is None:
+            viewmat, K = viewmat.contiguous().float().view(4, 4), K.contiguous().float().view(3, 3)
+        else:
+            viewmat = K = None
         n = means.shape[0]
         sh_bases = 1 + sh_rest.shape[1]
         if n == 0:
@@ -196,7 +214,7 @@ class _DnRasterize(torch.autograd.Function):
         if s.render_normals:
             if c2w is None:
                 raise L.DnrError("render_normals=True needs the camera_to_world matrix")
-            c2w = c2w.contiguous().float().view(3, 4)
+            c2w = None if host_cam is not None else c2w.contiguous().float().view(3, 4)
         H, W = s.height, s.width
         tiles_x, tiles_y = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
         n_tiles = tiles_x * tiles_y
@@ -218,6 +236,7 @@ class _DnRasterize(torch.autograd.Function):
         n_isects_dev = torch.empty(1, dtype=torch.int64, device=dev)
 
         a = _base_args(s, n, sh_bases)
+        _set_host_cam(a, host_cam)
         _set(a, viewmat=viewmat, K=K, c2w=c2w, means=means, quats=quats, scales=scales, opacities=opac, sh_dc=sh_dc,
              sh_rest=sh_rest if sh_bases > 1 else None, radii=radii, means2d=means2d, depths=depths, conics=conics,
              opac_act=opac_act, compensations=comp, colors=colors,
@@ -262,7 +281,7 @@ class _DnRasterize(torch.autograd.Function):
         L.check(_timed("raster_fwd", lib.dnr_raster_fwd, C.byref(a), st), "dnr_raster_fwd")
         L.check(_timed("finalize_fwd", lib.dnr_finalize_fwd, C.byref(a), st), "dnr_finalize_fwd")
 
-        ctx.settings, ctx.n, ctx.sh_bases, ctx.n_isects = s, n, sh_bases, n_isects
+        ctx.settings, ctx.n, ctx.sh_bases, ctx.n_isects, ctx.host_cam = s, n, sh_bases, n_isects, host_cam
         ctx.save_for_backward(means, quats, scales, opac, sh_dc, sh_rest, viewmat, K, c2w if s.render_normals else None)
         ctx.state = dict(radii=radii, records=records, flatten_ids=flatten_ids, tile_offsets=tile_offsets,
                          out_depth=out_depth, out_alpha=out_alpha, out_normal=out_normal, last_ids=last_ids,
@@ -297,6 +316,7 @@ class _DnRasterize(torch.autograd.Function):
         v_normal = prep(v_normal) if s.render_normals else None
         grad_records = torch.empty(n, L.GRAD_FLOATS, **f32)
         a = _base_args(s, n, ctx.sh_bases)
+        _set_host_cam(a, ctx.host_cam)
         a.n_isects = ctx.n_isects
         _set(a, viewmat=viewmat, K=K, c2w=c2w, means=means, quats=quats, scales=scales, opacities=opac, sh_dc=sh_dc,
              sh_rest=sh_rest if ctx.sh_bases > 1 else None, radii=S["radii"], records=S["records"],

@@ -21,16 +21,17 @@ def normal_from_depth_image(depths: Tensor, fx: float, fy: float, cx: float, cy:
     if depths.device.type != "cuda":
         raise L.DnrError("normal_from_depth_image: CUDA tensor required (no CPU path)")
     d = depths.detach().float().contiguous().view(H, W)
-    K = torch.tensor([[fx, 0.0, cx], [0.0, fy, cy], [0.0, 0.0, 1.0]], dtype=torch.float32).to(d.device, non_blocking=True)
     out = torch.empty(H, W, 3, dtype=torch.float32, device=d.device)
     a = L.DnrArgs()
     a.width, a.height = W, H
-    a.out_depth, a.out_surface_normal, a.K = d.data_ptr(), out.data_ptr(), K.data_ptr()
+    a.flags = L.FLAG_HOST_CAMERA  # intrinsics by value: no upload
+    a.host_cam[16], a.host_cam[17], a.host_cam[18], a.host_cam[19] = float(fx), float(fy), float(cx), float(cy)
+    a.out_depth, a.out_surface_normal = d.data_ptr(), out.data_ptr()
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     L.check(L.load().dnr_normal_from_depth(C.byref(a), st), "dnr_normal_from_depth")
-    if c2w is not None:
+    if c2w is not None and c2w.device.type == "cpu":  # identity test on the host only (a device tensor would sync)
         R = c2w[..., :3, :3].to(out)
-        if not bool(torch.equal(R.cpu(), torch.eye(3))):
+        if not bool(torch.equal(c2w[..., :3, :3].float(), torch.eye(3))):
             # means3d @ inv(R) + t  =>  differences (and hence normals) are rotated by inv(R)
             out = torch.nn.functional.normalize(out @ torch.linalg.inv(R), dim=-1) * (out.norm(dim=-1, keepdim=True) > 0)
     return out

@@ -49,6 +49,7 @@ extern "C" {
 #define DNR_FLAG_ANTIALIASED 2u /* rasterize_mode == "antialiased": opacity *= compensation */
 #define DNR_FLAG_NORMALS 4u     /* predict_normals: render the per-Gaussian normal channels */
 #define DNR_FLAG_ACCUMULATE 8u  /* project_bwd adds into the parameter-gradient buffers */
+#define DNR_FLAG_HOST_CAMERA 32u /* camera passed by value in host_cam[] (no device reads, no H2D copy) */
 #define DNR_FLAG_EXACT_LISTS 16u /* parity mode: emit gsplat's full bbox intersection lists (no precise-hit cull) */
 
 /* floats per packed per-Gaussian raster record, without / with normals */
@@ -144,6 +145,8 @@ typedef struct DnrArgs {
   float depth_lambda, depth_tolerance;
   int32_t depth_loss_type; /* 0 none, 1 EdgeAwareLogL1, 2 LogL1, 3 L1, 4 MSE */
   int32_t use_normal_loss;
+  /* with DNR_FLAG_HOST_CAMERA: [0..15] viewmat, [16..19] fx fy cx cy, [20..31] c2w[3,4]; viewmat/K/c2w pointers unused */
+  float host_cam[32];
 } DnrArgs;
 
 int dnr_version(void);

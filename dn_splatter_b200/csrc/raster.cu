@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(256) raster_bwd_kernel(const DnrArgs a, int ti
   const int nchunks = (n + CH - 1) / CH;
 
   float T = T_final;
-  float b0 = 0.f, b1 = 0.f, b2 = 0.f, bD = 0.f, bn0 = 0.f, bn1 = 0.f, bn2 = 0.f;
+  float S_cd = 0.f, S_n = 0.f;
+  const float Tf_va_cd = T_final * va_cd, Tf_va_n = T_final * va_n;
 
   // chunk c covers absolute indices [chi - n_c, chi), chi = hi - c*CH; slot t <-> index chi-1-t
   auto issue = [&](int c) {
@@ -321,26 +322,31 @@ __global__ void __launch_bounds__(256) raster_bwd_kernel(const DnrArgs a, int ti
       if (valid) {
         const float4 q2 = r4[t * (REC / 4) + 2];
         const float opac = q1.y;
-        const float ra = 1.0f / (1.0f - alpha);
+        float ra;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.0f - alpha));
         T *= ra;
         const float fac = alpha * T;
+        // d(out)/d(alpha_i) = sum_k (c_k T - B_k ra) v_k + T_final ra v_a with B_k = sum_{j>i} c_jk fac_j.  Only the
+        // contraction S = sum_k B_k v_k is needed, so one running scalar per gradient route replaces 7 buffers.
+        const float dot_cd = q2.x * vC0 + q2.y * vC1 + q2.z * vC2 + q2.w * vD;
+        const float v_alpha_cd = fmaf(T, dot_cd, ra * (Tf_va_cd - S_cd));
+        S_cd = fmaf(fac, dot_cd, S_cd);
         v[8] = fac * vC0; v[9] = fac * vC1; v[10] = fac * vC2; v[11] = fac * vD;
-        float v_alpha_cd = (q2.x * T - b0 * ra) * vC0 + (q2.y * T - b1 * ra) * vC1 + (q2.z * T - b2 * ra) * vC2 +
-                           (q2.w * T - bD * ra) * vD + T_final * ra * va_cd;
         float v_alpha_n = 0.f;
-        b0 += q2.x * fac; b1 += q2.y * fac; b2 += q2.z * fac; bD += q2.w * fac;
         if (NORMALS) {
           const float4 q3 = r4[t * (REC / 4) + 3];
+          const float dot_n = q3.x * vN0 + q3.y * vN1 + q3.z * vN2;
+          v_alpha_n = fmaf(T, dot_n, ra * (Tf_va_n - S_n));
+          S_n = fmaf(fac, dot_n, S_n);
           v[12] = fac * vN0; v[13] = fac * vN1; v[14] = fac * vN2;
-          v_alpha_n = (q3.x * T - bn0 * ra) * vN0 + (q3.y * T - bn1 * ra) * vN1 + (q3.z * T - bn2 * ra) * vN2 +
-                      T_final * ra * va_n;
-          bn0 += q3.x * fac; bn1 += q3.y * fac; bn2 += q3.z * fac;
         }
         if (opac * vis <= DNR_ALPHA_MAX) {
           const float v_alpha_all = v_alpha_cd + v_alpha_n;
-          const float vs_cd = -opac * vis * v_alpha_cd;   // d/d sigma
-          const float vs_all = -opac * vis * v_alpha_all;
-          v[4] = 0.5f * vs_all * dx * dx;
+          const float ov = opac * vis;
+          const float vs_cd = -ov * v_alpha_cd;   // d/d sigma
+          const float vs_all = -ov * v_alpha_all;
+          const float hx = 0.5f * vs_all * dx;
+          v[4] = hx * dx;
           v[5] = vs_all * dx * dy;
           v[6] = 0.5f * vs_all * dy * dy;
           // d sigma / d mean2d = (A dx + B dy, B dx + C dy) with A = -2 ln2 a', B = -ln2 b', C = -2 ln2 c'

@@ -50,7 +50,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", s, "-o", o]
+            defs = [f"-D{k}={os.environ[k]}" for k in ("DNR_BWD_PPT",) if k in os.environ]  # tuning knobs
+            cmd = [nvcc, *ARCH, *COMMON, *extra, *defs, "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)

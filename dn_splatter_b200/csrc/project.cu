@@ -62,6 +62,8 @@ __device__ __forceinline__ void quat_rot(const float q[4], float R[3][3], float 
 
 // SH basis values for a unit direction (Sloan's polynomial form; gsplat spherical_harmonics [EXT]).
 __device__ __forceinline__ void sh_basis(int degree, float x, float y, float z, float b[16]) {
+#pragma unroll
+  for (int k = 1; k < 16; ++k) b[k] = 0.f;
   b[0] = 0.2820947917738781f;
   if (degree < 1) return;
   b[1] = -0.48860251190292f * y;
@@ -250,7 +252,9 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const DnrArgs a) {
   float nw[3] = {0.f, 0.f, 0.f}, nc[3] = {0.f, 0.f, 0.f};
   if (NORMALS) {
     const int idx = argmin3(a.scales[i * 3 + 0], a.scales[i * 3 + 1], a.scales[i * 3 + 2]);
-    float n[3] = {g.R[0][idx], g.R[1][idx], g.R[2][idx]};
+    float n[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) n[r] = idx == 0 ? g.R[r][0] : (idx == 1 ? g.R[r][1] : g.R[r][2]);
     const float nn = fmaxf(sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]), 1e-12f);
     float vd[3];
 #pragma unroll
@@ -306,16 +310,19 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const DnrArgs a) {
     const float inorm = 1.0f / sqrtf((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]);
     sh_basis(deg, dir[0] * inorm, dir[1] * inorm, dir[2] * inorm, basis);
   } else {
-    basis[0] = 0.2820947917738781f;
+    sh_basis(0, 0.f, 0.f, 1.f, basis);
   }
   const int nb = (deg + 1) * (deg + 1);
   float col[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) col[c] = basis[0] * a.sh_dc[i * 3 + c];
   const float* rest = a.sh_rest + (size_t)i * (a.sh_bases - 1) * 3;
-  for (int k = 1; k < nb; ++k) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) col[c] += basis[k] * rest[(k - 1) * 3 + c];
+  for (int k = 1; k < 16; ++k) {
+    if (k < nb) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) col[c] += basis[k] * rest[(k - 1) * 3 + c];
+    }
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) col[c] = fmaxf(col[c] + 0.5f, 0.0f);
@@ -344,26 +351,35 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const DnrArgs a) {
 // backward: raster-gradient record -> parameter gradients (gsplat fully_fused_projection_bwd +
 // spherical_harmonics bwd + activation / normal chain rules).
 // ------------------------------------------------------------------------------------------------
+constexpr int PB_THREADS = 128;   // Gaussians per CTA in project_bwd
+constexpr int PB_REST_MAX = 45;    // (16 - 1) * 3 floats of higher-order SH gradient per Gaussian
+
+// The 180 B/Gaussian SH-gradient rows are staged in shared memory (stride 45 words: conflict-free) and written
+// by the whole CTA as one contiguous, coalesced stream instead of 45 strided 4-byte stores per thread.
 template <bool NORMALS>
-__global__ void __launch_bounds__(256) project_bwd_kernel(const DnrArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n_gauss) return;
+__global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(const DnrArgs a) {
+  __shared__ float s_rest[PB_THREADS * PB_REST_MAX];
+  __shared__ unsigned char s_vis[PB_THREADS];
+  const int i = blockIdx.x * PB_THREADS + threadIdx.x;
   const bool acc = (a.flags & DNR_FLAG_ACCUMULATE) != 0;
   const int nrest = a.sh_bases - 1;
-  const int radius = a.radii[i];
+  const int nrow = nrest * 3;
+  const bool in_range = i < a.n_gauss;
+  const int radius = in_range ? a.radii[i] : 0;
+  const bool visible = radius > 0;
+  s_vis[threadIdx.x] = visible ? 1 : 0;
+  float* srow = s_rest + threadIdx.x * PB_REST_MAX;
+#pragma unroll
+  for (int k = 0; k < PB_REST_MAX; ++k) srow[k] = 0.f;
   float vm[3] = {0, 0, 0}, vq[4] = {0, 0, 0, 0}, vs[3] = {0, 0, 0}, vo = 0.f, vdc[3] = {0, 0, 0};
-  float* vrest = a.v_sh_rest + (size_t)i * nrest * 3;
-  if (radius <= 0) {
-    if (!acc) {
-      for (int k = 0; k < 3; ++k) { a.v_means[i * 3 + k] = 0.f; a.v_scales[i * 3 + k] = 0.f; a.v_sh_dc[i * 3 + k] = 0.f; }
-      for (int k = 0; k < 4; ++k) a.v_quats[i * 4 + k] = 0.f;
-      a.v_opacities[i] = 0.f;
-      for (int k = 0; k < nrest * 3; ++k) vrest[k] = 0.f;
-      if (a.v_means2d) { a.v_means2d[i * 2] = 0.f; a.v_means2d[i * 2 + 1] = 0.f; }
-      if (a.v_means2d_abs) { a.v_means2d_abs[i * 2] = 0.f; a.v_means2d_abs[i * 2 + 1] = 0.f; }
-    }
-    return;
+  if (in_range && !visible && !acc) {
+    for (int k = 0; k < 3; ++k) { a.v_means[i * 3 + k] = 0.f; a.v_scales[i * 3 + k] = 0.f; a.v_sh_dc[i * 3 + k] = 0.f; }
+    for (int k = 0; k < 4; ++k) a.v_quats[i * 4 + k] = 0.f;
+    a.v_opacities[i] = 0.f;
+    if (a.v_means2d) { a.v_means2d[i * 2] = 0.f; a.v_means2d[i * 2 + 1] = 0.f; }
+    if (a.v_means2d_abs) { a.v_means2d_abs[i * 2] = 0.f; a.v_means2d_abs[i * 2 + 1] = 0.f; }
   }
+  if (visible) {
   Cam cam;
   load_cam(a, cam);
   Geo g;
@@ -468,7 +484,9 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const DnrArgs a) {
   if (NORMALS) {
     const float v_nc[3] = {g3.x, g3.y, g3.z};
     const int idx = argmin3(a.scales[i * 3 + 0], a.scales[i * 3 + 1], a.scales[i * 3 + 2]);
-    float n[3] = {g.R[0][idx], g.R[1][idx], g.R[2][idx]};
+    float n[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) n[r] = idx == 0 ? g.R[r][0] : (idx == 1 ? g.R[r][1] : g.R[r][2]);
     const float nn = fmaxf(sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]), 1e-12f);
     float vd[3], nu[3];
 #pragma unroll
@@ -506,44 +524,40 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const DnrArgs a) {
     const int deg = a.sh_degree;
     const int nb = (deg + 1) * (deg + 1);
     float basis[16];
-    float inorm = 1.f, ux = 0.f, uy = 0.f, uz = 0.f;
+    float inorm = 1.f, ux = 0.f, uy = 0.f, uz = 1.f;
     if (deg > 0) {
       inorm = 1.0f / sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
       ux = dir[0] * inorm; uy = dir[1] * inorm; uz = dir[2] * inorm;
-      sh_basis(deg, ux, uy, uz, basis);
-    } else {
-      basis[0] = 0.2820947917738781f;
     }
+    sh_basis(deg, ux, uy, uz, basis);
     const float* rest = a.sh_rest + (size_t)i * nrest * 3;
     // clamp mask: recompute the pre-clamp colour
-    float col[3];
+    float col[3], gk[16];
 #pragma unroll
     for (int c = 0; c < 3; ++c) col[c] = basis[0] * a.sh_dc[i * 3 + c];
-    for (int k = 1; k < nb; ++k)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) col[c] += basis[k] * rest[(k - 1) * 3 + c];
+    for (int k = 1; k < 16; ++k) {
+      if (k < nb) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) col[c] += basis[k] * rest[(k - 1) * 3 + c];
+      }
+    }
     float vc[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) vc[c] = (col[c] + 0.5f >= 0.0f) ? v_col[c] : 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) vdc[c] = basis[0] * vc[c];
-    float gk[16];
     gk[0] = 0.f;
-    for (int k = 1; k < nb; ++k) {
-      const float r0 = rest[(k - 1) * 3 + 0], r1 = rest[(k - 1) * 3 + 1], r2 = rest[(k - 1) * 3 + 2];
-      gk[k] = r0 * vc[0] + r1 * vc[1] + r2 * vc[2];
-      if (acc) {
-        vrest[(k - 1) * 3 + 0] += basis[k] * vc[0];
-        vrest[(k - 1) * 3 + 1] += basis[k] * vc[1];
-        vrest[(k - 1) * 3 + 2] += basis[k] * vc[2];
-      } else {
-        vrest[(k - 1) * 3 + 0] = basis[k] * vc[0];
-        vrest[(k - 1) * 3 + 1] = basis[k] * vc[1];
-        vrest[(k - 1) * 3 + 2] = basis[k] * vc[2];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+      gk[k] = 0.f;
+      if (k < nb) gk[k] = rest[(k - 1) * 3 + 0] * vc[0] + rest[(k - 1) * 3 + 1] * vc[1] + rest[(k - 1) * 3 + 2] * vc[2];  // L1 hit
+      if (k <= nrest) {
+        srow[(k - 1) * 3 + 0] = basis[k] * vc[0];
+        srow[(k - 1) * 3 + 1] = basis[k] * vc[1];
+        srow[(k - 1) * 3 + 2] = basis[k] * vc[2];
       }
     }
-    if (!acc)
-      for (int k = nb; k <= nrest; ++k) { vrest[(k - 1) * 3 + 0] = 0.f; vrest[(k - 1) * 3 + 1] = 0.f; vrest[(k - 1) * 3 + 2] = 0.f; }
     if (deg > 0) {
       float vu[3];
       sh_basis_vjp(deg, ux, uy, uz, gk, vu);
@@ -561,6 +575,24 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const DnrArgs a) {
     for (int k = 0; k < 3; ++k) { a.v_means[i * 3 + k] = vm[k]; a.v_scales[i * 3 + k] = vs[k]; a.v_sh_dc[i * 3 + k] = vdc[k]; }
     for (int k = 0; k < 4; ++k) a.v_quats[i * 4 + k] = vq[k];
     a.v_opacities[i] = vo;
+  }
+  }  // visible
+  __syncthreads();
+  if (nrest > 0) {
+    const int g0 = blockIdx.x * PB_THREADS;
+    const int ng = min(PB_THREADS, a.n_gauss - g0);
+    float* out = a.v_sh_rest + (size_t)g0 * nrow;
+    if (!acc) {
+      // dense overwrite: the CTA's rows are one contiguous span of ng*nrow floats
+      for (int e = threadIdx.x; e < ng * nrow; e += PB_THREADS) out[e] = s_rest[(e / nrow) * PB_REST_MAX + e % nrow];
+    } else {
+      // accumulate only the visible rows (read-modify-write, coalesced per row)
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      for (int g = warp; g < ng; g += PB_THREADS / 32) {
+        if (!s_vis[g]) continue;
+        for (int e = lane; e < nrow; e += 32) out[(size_t)g * nrow + e] += s_rest[g * PB_REST_MAX + e];
+      }
+    }
   }
 }
 
@@ -599,7 +631,8 @@ extern "C" int dnr_project_bwd(const DnrArgs* a, void* stream) {
   if (a->sh_bases > 1 && (!a->sh_rest || !a->v_sh_rest)) return DNR_E_NULL;
   const bool normals = (a->flags & DNR_FLAG_NORMALS) != 0;
   if (normals && !hostcam && !a->c2w) return DNR_E_NULL;
-  const int block = 256, grid = (a->n_gauss + block - 1) / block;
+  if (a->sh_bases > 16) return DNR_E_OPTION;
+  const int block = PB_THREADS, grid = (a->n_gauss + block - 1) / block;
   cudaStream_t s = (cudaStream_t)stream;
   if (normals) project_bwd_kernel<true><<<grid, block, 0, s>>>(*a);
   else project_bwd_kernel<false><<<grid, block, 0, s>>>(*a);

@@ -19,6 +19,9 @@
 
 namespace {
 
+#ifndef DNR_BWD_PPT
+#define DNR_BWD_PPT 2      // pixels per thread in raster_bwd (1 or 2)
+#endif
 constexpr int CH = 128;   // records per chunk
 constexpr int STAGES = 2;
 
@@ -204,61 +207,81 @@ __device__ __forceinline__ void butterfly16(float (&v)[16], int lane) {
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-template <bool NORMALS>
-__global__ void __launch_bounds__(256) raster_bwd_kernel(const DnrArgs a, int tiles_x) {
+// PPT pixels per thread: 256/PPT threads per tile.  With PPT = 2 a warp covers an 8x8 patch and the 16-value
+// butterfly + RED (the largest fixed cost per record) is paid once per 64 pixels instead of once per 32.
+template <bool NORMALS, int PPT>
+__global__ void __launch_bounds__(256 / PPT) raster_bwd_kernel(const DnrArgs a, int tiles_x) {
   constexpr int REC = NORMALS ? DNR_REC_FLOATS_N : DNR_REC_FLOATS;
+  constexpr int NT = 256 / PPT;   // threads per tile
+  constexpr int NW = NT / 32;     // warps per tile
   __shared__ __align__(128) float recs[STAGES][CH * REC];
   __shared__ int ids_s[STAGES][CH];
   __shared__ __align__(8) uint64_t bars[STAGES];
-  __shared__ int red_last[8];
+  __shared__ int red_last[NW];
 
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.y * tiles_x + blockIdx.x;
-  int lx, ly;
-  pixel_of_thread(tid, lx, ly);
-  const int j = blockIdx.x * DNR_TILE + lx, i = blockIdx.y * DNR_TILE + ly;
-  const bool inside = (i < a.height) && (j < a.width);
-  const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-  const int pix = inside ? i * a.width + j : 0;
   const int start = a.tile_offsets[tile], end = a.tile_offsets[tile + 1];
 
   // ---- per-pixel state and the gradient of the glue (P1/P3 backward) ----
-  const int last_id = inside ? a.last_ids[pix] : -1;
-  float T_final = 1.f, vC0 = 0.f, vC1 = 0.f, vC2 = 0.f, vD = 0.f, va_cd = 0.f;
-  float vN0 = 0.f, vN1 = 0.f, vN2 = 0.f, va_n = 0.f;
-  if (inside) {
-    const float alpha = a.out_alpha[pix];
-    T_final = 1.0f - alpha;
-    if (a.v_rgb) {
-      const uint8_t m = a.clamp_mask[pix];
-      vC0 = (m & 1) ? a.v_rgb[pix * 3 + 0] : 0.f;
-      vC1 = (m & 2) ? a.v_rgb[pix * 3 + 1] : 0.f;
-      vC2 = (m & 4) ? a.v_rgb[pix * 3 + 2] : 0.f;
-      va_cd -= a.background[0] * vC0 + a.background[1] * vC1 + a.background[2] * vC2;
+  float px[PPT], py[PPT], T_final[PPT], vC0[PPT], vC1[PPT], vC2[PPT], vD[PPT], vN0[PPT], vN1[PPT], vN2[PPT];
+  float Tf_va_cd[PPT], Tf_va_n[PPT];
+  int last_id[PPT];
+  bool inside[PPT];
+  int wl = -1;
+#pragma unroll
+  for (int p = 0; p < PPT; ++p) {
+    int lx, ly;
+    if (PPT == 1) {
+      pixel_of_thread(tid, lx, ly);
+    } else {  // warp -> 8 wide x (4*PPT) tall patch; the thread's pixels are 4 rows apart
+      lx = ((warp & 1) << 3) + (lane & 7);
+      ly = (warp >> 1) * (4 * PPT) + (lane >> 3) + 4 * p;
     }
-    if (a.v_alpha) va_cd += a.v_alpha[pix];
-    if (a.v_depth && alpha > 0.f) {
-      const float v_ed = a.v_depth[pix];
-      const float ac = fmaxf(alpha, 1e-10f);
-      vD = v_ed / ac;
-      if (alpha >= 1e-10f) va_cd -= v_ed * a.out_depth[pix] / ac;
+    const int j = blockIdx.x * DNR_TILE + lx, i = blockIdx.y * DNR_TILE + ly;
+    inside[p] = (i < a.height) && (j < a.width);
+    px[p] = (float)j + 0.5f; py[p] = (float)i + 0.5f;
+    const int pix = inside[p] ? i * a.width + j : 0;
+    last_id[p] = inside[p] ? a.last_ids[pix] : -1;
+    wl = max(wl, last_id[p]);
+    T_final[p] = 1.f;
+    vC0[p] = vC1[p] = vC2[p] = vD[p] = vN0[p] = vN1[p] = vN2[p] = 0.f;
+    float va_cd = 0.f, va_n = 0.f;
+    if (inside[p]) {
+      const float alpha = a.out_alpha[pix];
+      T_final[p] = 1.0f - alpha;
+      if (a.v_rgb) {
+        const uint8_t m = a.clamp_mask[pix];
+        vC0[p] = (m & 1) ? a.v_rgb[pix * 3 + 0] : 0.f;
+        vC1[p] = (m & 2) ? a.v_rgb[pix * 3 + 1] : 0.f;
+        vC2[p] = (m & 4) ? a.v_rgb[pix * 3 + 2] : 0.f;
+        va_cd -= a.background[0] * vC0[p] + a.background[1] * vC1[p] + a.background[2] * vC2[p];
+      }
+      if (a.v_alpha) va_cd += a.v_alpha[pix];
+      if (a.v_depth && alpha > 0.f) {
+        const float v_ed = a.v_depth[pix];
+        const float ac = fmaxf(alpha, 1e-10f);
+        vD[p] = v_ed / ac;
+        if (alpha >= 1e-10f) va_cd -= v_ed * a.out_depth[pix] / ac;
+      }
+      if (NORMALS && a.v_normal) {
+        const float nn = a.normal_norm[pix];
+        const float n0 = 2.0f * a.out_normal[pix * 3 + 0] - 1.0f, n1 = 2.0f * a.out_normal[pix * 3 + 1] - 1.0f,
+                    n2 = 2.0f * a.out_normal[pix * 3 + 2] - 1.0f;
+        const float g0 = 0.5f * a.v_normal[pix * 3 + 0], g1 = 0.5f * a.v_normal[pix * 3 + 1], g2 = 0.5f * a.v_normal[pix * 3 + 2];
+        const float dp = n0 * g0 + n1 * g1 + n2 * g2;
+        vN0[p] = (g0 - n0 * dp) / nn; vN1[p] = (g1 - n1 * dp) / nn; vN2[p] = (g2 - n2 * dp) / nn;
+        va_n = -(vN0[p] + vN1[p] + vN2[p]);
+      }
     }
-    if (NORMALS && a.v_normal) {
-      const float nn = a.normal_norm[pix];
-      const float n0 = 2.0f * a.out_normal[pix * 3 + 0] - 1.0f, n1 = 2.0f * a.out_normal[pix * 3 + 1] - 1.0f,
-                  n2 = 2.0f * a.out_normal[pix * 3 + 2] - 1.0f;
-      const float g0 = 0.5f * a.v_normal[pix * 3 + 0], g1 = 0.5f * a.v_normal[pix * 3 + 1], g2 = 0.5f * a.v_normal[pix * 3 + 2];
-      const float dp = n0 * g0 + n1 * g1 + n2 * g2;
-      vN0 = (g0 - n0 * dp) / nn; vN1 = (g1 - n1 * dp) / nn; vN2 = (g2 - n2 * dp) / nn;
-      va_n = -(vN0 + vN1 + vN2);
-    }
+    Tf_va_cd[p] = T_final[p] * va_cd;
+    Tf_va_n[p] = T_final[p] * va_n;
   }
 
   // ---- range actually composited by this tile ----
-  int wl = last_id;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
-  if (lane == 0) red_last[tid >> 5] = wl;
+  if (lane == 0) red_last[warp] = wl;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -267,15 +290,15 @@ __global__ void __launch_bounds__(256) raster_bwd_kernel(const DnrArgs a, int ti
   __syncthreads();
   int hi = red_last[0];
 #pragma unroll
-  for (int w = 1; w < 8; ++w) hi = max(hi, red_last[w]);
+  for (int w = 1; w < NW; ++w) hi = max(hi, red_last[w]);
   hi = min(hi + 1, end);  // exclusive
   const int n = hi - start;
   if (n <= 0) return;
   const int nchunks = (n + CH - 1) / CH;
 
-  float T = T_final;
-  float S_cd = 0.f, S_n = 0.f;
-  const float Tf_va_cd = T_final * va_cd, Tf_va_n = T_final * va_n;
+  float T[PPT], S_cd[PPT], S_n[PPT];
+#pragma unroll
+  for (int p = 0; p < PPT; ++p) { T[p] = T_final[p]; S_cd[p] = 0.f; S_n[p] = 0.f; }
 
   // chunk c covers absolute indices [chi - n_c, chi), chi = hi - c*CH; slot t <-> index chi-1-t
   auto issue = [&](int c) {
@@ -283,10 +306,10 @@ __global__ void __launch_bounds__(256) raster_bwd_kernel(const DnrArgs a, int ti
     const int n_c = min(CH, chi - start);
     const int stage = c & 1;
     if (tid == 0) mbar_arrive_expect_tx(&bars[stage], (uint32_t)(n_c * REC * 4));
-    if (tid < n_c) {
-      const int g = a.flatten_ids[chi - 1 - tid];
-      ids_s[stage][tid] = g;
-      bulk_g2s(recs[stage] + tid * REC, a.records + (size_t)g * REC, REC * 4, &bars[stage]);
+    for (int t = tid; t < n_c; t += NT) {
+      const int g = a.flatten_ids[chi - 1 - t];
+      ids_s[stage][t] = g;
+      bulk_g2s(recs[stage] + t * REC, a.records + (size_t)g * REC, REC * 4, &bars[stage]);
     }
   };
   issue(0);
@@ -300,62 +323,72 @@ __global__ void __launch_bounds__(256) raster_bwd_kernel(const DnrArgs a, int ti
     const float4* r4 = reinterpret_cast<const float4*>(recs[stage]);
     for (int t = 0; t < n_c; ++t) {
       const int idx = chi - 1 - t;
-      bool valid = inside && (idx <= last_id);
-      float4 q0, q1;
-      float dx = 0.f, dy = 0.f, vis = 0.f, alpha = 0.f;
-      if (valid) {
-        q0 = r4[t * (REC / 4) + 0];
-        q1 = r4[t * (REC / 4) + 1];
-        dx = q0.x - px; dy = q0.y - py;
-        const float pw = dnr_power2(q0.z, q0.w, q1.x, dx, dy);
-        valid = !(pw > 0.f || pw < q1.z);
-        if (valid) {
-          vis = dnr_ex2(pw);
-          alpha = fminf(DNR_ALPHA_MAX, __fmul_rn(q1.y, vis));
-          valid = !(alpha < DNR_ALPHA_MIN);
+      const float4 q0 = r4[t * (REC / 4) + 0];
+      const float4 q1 = r4[t * (REC / 4) + 1];
+      bool valid[PPT];
+      float dx[PPT], dy[PPT], vis[PPT], alpha[PPT];
+      bool any = false;
+#pragma unroll
+      for (int p = 0; p < PPT; ++p) {
+        valid[p] = inside[p] && (idx <= last_id[p]);
+        dx[p] = q0.x - px[p]; dy[p] = q0.y - py[p];
+        vis[p] = 0.f; alpha[p] = 0.f;
+        if (valid[p]) {
+          const float pw = dnr_power2(q0.z, q0.w, q1.x, dx[p], dy[p]);
+          valid[p] = !(pw > 0.f || pw < q1.z);
+          if (valid[p]) {
+            vis[p] = dnr_ex2(pw);
+            alpha[p] = fminf(DNR_ALPHA_MAX, __fmul_rn(q1.y, vis[p]));
+            valid[p] = !(alpha[p] < DNR_ALPHA_MIN);
+          }
         }
+        any = any || valid[p];
       }
-      if (!__any_sync(0xffffffffu, valid)) continue;
+      if (!__any_sync(0xffffffffu, any)) continue;
       float v[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) v[k] = 0.f;
-      if (valid) {
+      if (any) {
         const float4 q2 = r4[t * (REC / 4) + 2];
+        float4 q3 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (NORMALS) q3 = r4[t * (REC / 4) + 3];
         const float opac = q1.y;
-        float ra;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.0f - alpha));
-        T *= ra;
-        const float fac = alpha * T;
-        // d(out)/d(alpha_i) = sum_k (c_k T - B_k ra) v_k + T_final ra v_a with B_k = sum_{j>i} c_jk fac_j.  Only the
-        // contraction S = sum_k B_k v_k is needed, so one running scalar per gradient route replaces 7 buffers.
-        const float dot_cd = q2.x * vC0 + q2.y * vC1 + q2.z * vC2 + q2.w * vD;
-        const float v_alpha_cd = fmaf(T, dot_cd, ra * (Tf_va_cd - S_cd));
-        S_cd = fmaf(fac, dot_cd, S_cd);
-        v[8] = fac * vC0; v[9] = fac * vC1; v[10] = fac * vC2; v[11] = fac * vD;
-        float v_alpha_n = 0.f;
-        if (NORMALS) {
-          const float4 q3 = r4[t * (REC / 4) + 3];
-          const float dot_n = q3.x * vN0 + q3.y * vN1 + q3.z * vN2;
-          v_alpha_n = fmaf(T, dot_n, ra * (Tf_va_n - S_n));
-          S_n = fmaf(fac, dot_n, S_n);
-          v[12] = fac * vN0; v[13] = fac * vN1; v[14] = fac * vN2;
-        }
-        if (opac * vis <= DNR_ALPHA_MAX) {
-          const float v_alpha_all = v_alpha_cd + v_alpha_n;
-          const float ov = opac * vis;
-          const float vs_cd = -ov * v_alpha_cd;   // d/d sigma
-          const float vs_all = -ov * v_alpha_all;
-          const float hx = 0.5f * vs_all * dx;
-          v[4] = hx * dx;
-          v[5] = vs_all * dx * dy;
-          v[6] = 0.5f * vs_all * dy * dy;
-          // d sigma / d mean2d = (A dx + B dy, B dx + C dy) with A = -2 ln2 a', B = -ln2 b', C = -2 ln2 c'
-          const float k = -DNR_LN2 * vs_cd;
-          v[0] = k * (2.0f * q0.z * dx + q0.w * dy);
-          v[1] = k * (q0.w * dx + 2.0f * q1.x * dy);
-          v[2] = fabsf(v[0]);
-          v[3] = fabsf(v[1]);
-          v[7] = vis * v_alpha_all;
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+          if (valid[p]) {
+            float ra;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.0f - alpha[p]));
+            T[p] *= ra;
+            const float fac = alpha[p] * T[p];
+            // d(out)/d(alpha_i) = sum_k (c_k T - B_k ra) v_k + T_final ra v_a, B_k = sum_{j>i} c_jk fac_j.  Only the
+            // contraction S = sum_k B_k v_k is needed: one running scalar per gradient route replaces 7 buffers.
+            const float dot_cd = q2.x * vC0[p] + q2.y * vC1[p] + q2.z * vC2[p] + q2.w * vD[p];
+            const float v_alpha_cd = fmaf(T[p], dot_cd, ra * (Tf_va_cd[p] - S_cd[p]));
+            S_cd[p] = fmaf(fac, dot_cd, S_cd[p]);
+            v[8] += fac * vC0[p]; v[9] += fac * vC1[p]; v[10] += fac * vC2[p]; v[11] += fac * vD[p];
+            float v_alpha_n = 0.f;
+            if (NORMALS) {
+              const float dot_n = q3.x * vN0[p] + q3.y * vN1[p] + q3.z * vN2[p];
+              v_alpha_n = fmaf(T[p], dot_n, ra * (Tf_va_n[p] - S_n[p]));
+              S_n[p] = fmaf(fac, dot_n, S_n[p]);
+              v[12] += fac * vN0[p]; v[13] += fac * vN1[p]; v[14] += fac * vN2[p];
+            }
+            const float ov = opac * vis[p];
+            if (ov <= DNR_ALPHA_MAX) {
+              const float v_alpha_all = v_alpha_cd + v_alpha_n;
+              const float vs_cd = -ov * v_alpha_cd;   // d/d sigma
+              const float vs_all = -ov * v_alpha_all;
+              v[4] += 0.5f * vs_all * dx[p] * dx[p];
+              v[5] += vs_all * dx[p] * dy[p];
+              v[6] += 0.5f * vs_all * dy[p] * dy[p];
+              // d sigma / d mean2d = (A dx + B dy, B dx + C dy) with A = -2 ln2 a', B = -ln2 b', C = -2 ln2 c'
+              const float k = -DNR_LN2 * vs_cd;
+              const float gx = k * (2.0f * q0.z * dx[p] + q0.w * dy[p]);
+              const float gy = k * (q0.w * dx[p] + 2.0f * q1.x * dy[p]);
+              v[0] += gx; v[1] += gy; v[2] += fabsf(gx); v[3] += fabsf(gy);
+              v[7] += vis[p] * v_alpha_all;
+            }
+          }
         }
       }
       butterfly16(v, lane);
@@ -402,8 +435,9 @@ extern "C" int dnr_raster_bwd(const DnrArgs* a, void* stream) {
   DNR_CUDA(cudaMemsetAsync(a->grad_records, 0, (size_t)a->n_gauss * DNR_GRAD_FLOATS * sizeof(float), s));
   if (a->n_isects == 0) return 0;
   const dim3 grid(dnr_tiles_x(a), dnr_tiles_y(a));
-  if (normals) raster_bwd_kernel<true><<<grid, 256, 0, s>>>(*a, grid.x);
-  else raster_bwd_kernel<false><<<grid, 256, 0, s>>>(*a, grid.x);
+  constexpr int PPT = DNR_BWD_PPT;
+  if (normals) raster_bwd_kernel<true, PPT><<<grid, 256 / PPT, 0, s>>>(*a, grid.x);
+  else raster_bwd_kernel<false, PPT><<<grid, 256 / PPT, 0, s>>>(*a, grid.x);
   DNR_CHECK_LAUNCH();
   return 0;
 }

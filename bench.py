@@ -31,8 +31,6 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = "rendered Mpix/s (fwd+bwd, RGB+depth+normal)"
-HANDWRITTEN_LAUNCHES_PER_STEP = 13  # project_fwd iota emit offsets raster_fwd finalize loss_fwd loss_finish
-#                                     scale_loss_fwd | scale_loss_bwd loss_bwd raster_bwd project_bwd
 
 
 def parse():
@@ -323,7 +321,11 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    from dn_splatter_b200 import _lib as _L
+
+    launches0 = dict(_L.LAUNCHES)
     ms = timed(args.steps, resident_step)
+    launches = {k: _L.LAUNCHES[k] - launches0[k] for k in launches0}
     clocks = sampler.stop() if rank == 0 else None
     pix = args.width * args.height
     value = world * args.steps * pix / 1e6 / (ms / 1e3)
@@ -398,9 +400,9 @@ def main():
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, normals, world), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": HANDWRITTEN_LAUNCHES_PER_STEP * args.steps,
-            "gpu_launches_note": "hand-written dnr kernels only; each step also runs ~14 cub radix-sort/scan passes compiled into "
-                                 "libdnr_b200.so and ~12 torch element-wise kernels of the L1 photometric loss",
+            "gpu_launches": launches["handwritten"],
+            "gpu_launches_note": f"hand-written dnr kernels counted at the C-ABI calls of the timed region; the same calls ran "
+                                 f"{launches['cub']} cub radix-sort/scan passes (compiled into libdnr_b200.so)",
             "roofline": roof, "stages_ms": stages, "cpu_baseline": cpu, "last_loss": losses[-1] if losses else None,
         }
         print(json.dumps(line), flush=True)

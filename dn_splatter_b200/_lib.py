@@ -46,12 +46,42 @@ POINTER_FIELDS = {n for n, t in DnrArgs._fields_ if t is _p}
 
 _lib: Optional[C.CDLL] = None
 
+# hand-written kernels launched per C-ABI call (cub's radix-sort / scan passes are counted separately)
+KERNELS_PER_CALL = {
+    "dnr_project_fwd": (1, 0), "dnr_bin_scan": (2, 8), "dnr_bin_sort": (3, 4), "dnr_raster_fwd": (1, 0),
+    "dnr_finalize_fwd": (1, 0), "dnr_normal_from_depth": (1, 0), "dnr_raster_bwd": (1, 0), "dnr_project_bwd": (1, 0),
+    "dnr_loss_fwd": (2, 0), "dnr_loss_bwd": (1, 0), "dnr_scale_loss_fwd": (1, 0), "dnr_scale_loss_bwd": (1, 0),
+    "dnr_l1_fwd": (1, 0), "dnr_l1_bwd": (1, 0), "dnr_u8_to_f32": (1, 0),
+}
+LAUNCHES = {"handwritten": 0, "cub": 0}
+
+
+class _Counting:
+    """Thin proxy over the CDLL that counts kernel launches per call (bench.py's gpu_launches)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        k = KERNELS_PER_CALL.get(name)
+        if k is None:
+            return fn
+
+        def call(*args):
+            LAUNCHES["handwritten"] += k[0]
+            LAUNCHES["cub"] += k[1]
+            return fn(*args)
+
+        self.__dict__[name] = call
+        return call
+
 
 class DnrError(RuntimeError):
     pass
 
 
-def load() -> C.CDLL:
+def load():
     """Loads the shared library, failing loudly when it has not been built (python -m dn_splatter_b200.build)."""
     global _lib
     if _lib is not None:
@@ -79,18 +109,25 @@ def load() -> C.CDLL:
     lib.dnr_scale_loss_fwd.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.dnr_scale_loss_bwd.restype = C.c_int
     lib.dnr_scale_loss_bwd.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dnr_l1_fwd.restype = C.c_int
+    lib.dnr_l1_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.dnr_l1_bwd.restype = C.c_int
+    lib.dnr_l1_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dnr_u8_to_f32.restype = C.c_int
+    lib.dnr_u8_to_f32.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     lib.dnr_bin_scan_workspace_bytes.restype = C.c_size_t
     lib.dnr_bin_scan_workspace_bytes.argtypes = [C.c_int32]
     lib.dnr_bin_sort_workspace_bytes.restype = C.c_size_t
     lib.dnr_bin_sort_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32]
-    _lib = lib
-    return lib
+    _lib = _Counting(lib)
+    return _lib
 
 
 EXPORTS = (
     "dnr_version", "dnr_error_string", "dnr_project_fwd", "dnr_bin_scan_workspace_bytes", "dnr_bin_scan",
     "dnr_bin_sort_workspace_bytes", "dnr_bin_sort", "dnr_raster_fwd", "dnr_finalize_fwd", "dnr_normal_from_depth",
     "dnr_raster_bwd", "dnr_project_bwd", "dnr_loss_fwd", "dnr_loss_bwd", "dnr_scale_loss_fwd", "dnr_scale_loss_bwd",
+    "dnr_l1_fwd", "dnr_l1_bwd", "dnr_u8_to_f32",
 )
 
 

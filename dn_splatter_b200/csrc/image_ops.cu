@@ -237,6 +237,48 @@ __global__ void __launch_bounds__(256) scale_loss_bwd_kernel(const float* __rest
   v_scales[i * 3 + 2] = idx == 2 ? g : 0.f;
 }
 
+template <bool U8>
+__device__ __forceinline__ float gt_at(const void* gt, int64_t i) {
+  return U8 ? (float)((const uint8_t*)gt)[i] / 255.0f : ((const float*)gt)[i];
+}
+
+template <bool U8>
+__global__ void __launch_bounds__(256) l1_fwd_kernel(const float* __restrict__ pred, const void* __restrict__ gt, int64_t n,
+                                                    float* out) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += fabsf(pred[i] - gt_at<U8>(gt, i));
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out, t / (float)n);
+  }
+}
+
+template <bool U8>
+__global__ void __launch_bounds__(256) l1_bwd_kernel(const float* __restrict__ pred, const void* __restrict__ gt, int64_t n,
+                                                    const float* v_loss, float* __restrict__ v_pred) {
+  const float s = (v_loss ? __ldg(v_loss) : 1.0f) / (float)n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    v_pred[i] = sgn(pred[i] - gt_at<U8>(gt, i)) * s;
+}
+
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ src, int64_t n, float divisor, float lo,
+                                                       float* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = fmaxf((float)src[i] / divisor, lo);  // a true division, as image.float() / 255.0 in the reference
+}
+
+inline int stream_grid(int64_t n) {
+  const int64_t b = (n + 256 * 4 - 1) / (256 * 4);
+  return (int)(b < 148 * 8 ? (b > 0 ? b : 1) : 148 * 8);
+}
+
 inline dim3 img_grid(const DnrArgs* a) { return dim3((a->width + 31) / 32, (a->height + 7) / 8); }
 
 }  // namespace
@@ -305,6 +347,36 @@ extern "C" int dnr_scale_loss_bwd(const float* scales, int32_t n_gauss, const fl
   if (!scales || !v_scales) return DNR_E_NULL;
   if (n_gauss <= 0) return DNR_E_SIZE;
   scale_loss_bwd_kernel<<<(n_gauss + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scales, n_gauss, v_loss, v_scales);
+  DNR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dnr_l1_fwd(const float* pred, const void* gt, int64_t n, int32_t gt_is_u8, float* loss_out, void* stream) {
+  if (!pred || !gt || !loss_out) return DNR_E_NULL;
+  if (n <= 0) return DNR_E_SIZE;
+  cudaStream_t s = (cudaStream_t)stream;
+  DNR_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), s));
+  if (gt_is_u8) l1_fwd_kernel<true><<<stream_grid(n), 256, 0, s>>>(pred, gt, n, loss_out);
+  else l1_fwd_kernel<false><<<stream_grid(n), 256, 0, s>>>(pred, gt, n, loss_out);
+  DNR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dnr_l1_bwd(const float* pred, const void* gt, int64_t n, int32_t gt_is_u8, const float* v_loss, float* v_pred,
+                          void* stream) {
+  if (!pred || !gt || !v_pred) return DNR_E_NULL;
+  if (n <= 0) return DNR_E_SIZE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (gt_is_u8) l1_bwd_kernel<true><<<stream_grid(n), 256, 0, s>>>(pred, gt, n, v_loss, v_pred);
+  else l1_bwd_kernel<false><<<stream_grid(n), 256, 0, s>>>(pred, gt, n, v_loss, v_pred);
+  DNR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dnr_u8_to_f32(const uint8_t* src, int64_t n, float divisor, float clamp_min, float* dst, void* stream) {
+  if (!src || !dst) return DNR_E_NULL;
+  if (n <= 0) return DNR_E_SIZE;
+  u8_to_f32_kernel<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(src, n, divisor, clamp_min, dst);
   DNR_CHECK_LAUNCH();
   return 0;
 }

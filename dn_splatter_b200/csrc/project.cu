@@ -360,6 +360,8 @@ template <bool NORMALS>
 __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(const DnrArgs a) {
   __shared__ float s_rest[PB_THREADS * PB_REST_MAX];
   __shared__ unsigned char s_vis[PB_THREADS];
+  __shared__ unsigned char s_list[PB_THREADS];
+  __shared__ int s_nvis;
   const int i = blockIdx.x * PB_THREADS + threadIdx.x;
   const bool acc = (a.flags & DNR_FLAG_ACCUMULATE) != 0;
   const int nrest = a.sh_bases - 1;
@@ -586,11 +588,23 @@ __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(const DnrArgs a
       // dense overwrite: the CTA's rows are one contiguous span of ng*nrow floats
       for (int e = threadIdx.x; e < ng * nrow; e += PB_THREADS) out[e] = s_rest[(e / nrow) * PB_REST_MAX + e % nrow];
     } else {
-      // accumulate only the visible rows (read-modify-write, coalesced per row)
-      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-      for (int g = warp; g < ng; g += PB_THREADS / 32) {
-        if (!s_vis[g]) continue;
-        for (int e = lane; e < nrow; e += 32) out[(size_t)g * nrow + e] += s_rest[g * PB_REST_MAX + e];
+      // accumulate only the visible rows: compact their indices, then spread (row, element) pairs over the CTA so
+      // the read-modify-writes of different rows overlap (each row is a contiguous 4*nrow-byte span)
+      if (threadIdx.x < 32) {
+        int base = 0;
+        for (int g0l = 0; g0l < PB_THREADS; g0l += 32) {
+          const bool vz = (g0l + threadIdx.x < ng) && s_vis[g0l + threadIdx.x];
+          const unsigned m = __ballot_sync(0xffffffffu, vz);
+          if (vz) s_list[base + __popc(m & ((1u << threadIdx.x) - 1u))] = (unsigned char)(g0l + threadIdx.x);
+          base += __popc(m);
+        }
+        if (threadIdx.x == 0) s_nvis = base;
+      }
+      __syncthreads();
+      const int total = s_nvis * nrow;
+      for (int e = threadIdx.x; e < total; e += PB_THREADS) {
+        const int r = s_list[e / nrow], k = e % nrow;
+        out[(size_t)r * nrow + k] += s_rest[r * PB_REST_MAX + k];
       }
     }
   }

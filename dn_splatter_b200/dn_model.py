@@ -21,7 +21,7 @@ from torch import Tensor
 from .cameras import Cameras, is_camera
 from .losses import DepthLoss, DepthLossType, TVLoss
 from .rasterize import dn_rasterize, get_viewmat, to_device_async
-from .regularization_strategy import AGSMeshRegularization, DNRegularization
+from .regularization_strategy import AGSMeshRegularization, DNRegularization, FusedL1, u8_to_float
 from .utils.normal_utils import normal_from_depth_image
 
 SH_C0 = 0.28209479177387814
@@ -328,10 +328,15 @@ class DNSplatterModel(torch.nn.Module):
             return F.interpolate(image.permute(2, 0, 1)[None].float(), size=(h, w), mode="bilinear", antialias=True)[0].permute(1, 2, 0)
         return image
 
-    def get_gt_img(self, image: Tensor) -> Tensor:
+    def get_gt_img(self, image: Tensor, clamp_min: float = 0.0) -> Tensor:
         if image.dtype == torch.uint8:
-            image = image.float() / 255.0
-        return self._downscale_if_required(image).to(self.device)
+            if image.device.type == "cuda":
+                image = u8_to_float(image, 255.0, clamp_min)  # one kernel instead of float() / 255 (/ clamp)
+                clamp_min = 0.0
+            else:
+                image = image.float() / 255.0
+        image = self._downscale_if_required(image).to(self.device)
+        return image.clamp(min=clamp_min) if clamp_min > 0.0 else image
 
     def composite_with_background(self, image: Tensor, background: Tensor) -> Tensor:
         if image.shape[2] == 4:
@@ -427,13 +432,20 @@ class DNSplatterModel(torch.nn.Module):
     def _rgb_loss_dict(self, outputs, batch) -> Dict[str, Tensor]:
         """SplatfactoModel.get_loss_dict [EXT nerfstudio 1.1.3]: (1-l) L1 + l (1-SSIM), optional scale reg."""
         cfg = self.config
-        gt_img = self.composite_with_background(self.get_gt_img(batch["image"]), outputs["background"])
         pred_img = outputs["rgb"]
-        if "mask" in batch:
-            mask = self._downscale_if_required(batch["mask"]).to(self.device)
-            assert mask.shape[:2] == gt_img.shape[:2] == pred_img.shape[:2]
-            gt_img, pred_img = gt_img * mask, pred_img * mask
-        l1 = torch.abs(gt_img - pred_img).mean()
+        img = batch["image"]
+        fused = ("mask" not in batch and img.shape[-1] == 3 and img.device == pred_img.device and pred_img.is_cuda
+                 and self._get_downscale_factor() == 1 and cfg.ssim_lambda == 0)
+        if fused:  # photometric L1 straight from the (uint8) image: one kernel each way
+            l1 = FusedL1.apply(pred_img, img)
+            gt_img = None
+        else:
+            gt_img = self.composite_with_background(self.get_gt_img(img), outputs["background"])
+            if "mask" in batch:
+                mask = self._downscale_if_required(batch["mask"]).to(self.device)
+                assert mask.shape[:2] == gt_img.shape[:2] == pred_img.shape[:2]
+                gt_img, pred_img = gt_img * mask, pred_img * mask
+            l1 = torch.abs(gt_img - pred_img).mean()
         main = (1 - cfg.ssim_lambda) * l1
         if cfg.ssim_lambda > 0:
             main = main + cfg.ssim_lambda * (1 - ssim(gt_img.permute(2, 0, 1)[None], pred_img.permute(2, 0, 1)[None]))
@@ -449,7 +461,7 @@ class DNSplatterModel(torch.nn.Module):
         cfg = self.config
         loss_dict = self._rgb_loss_dict(outputs, batch)
         rgb_loss, scale_reg = loss_dict["main_loss"], loss_dict["scale_reg"]
-        gt_img = self.get_gt_img(batch["image"]).clamp(min=10 / 255.0)  # quirk B10
+        gt_img = self.get_gt_img(batch["image"], clamp_min=10 / 255.0)  # quirk B10
         depth_out = outputs["depth"]
         sensor_depth_gt = self.get_gt_img(batch["sensor_depth"]) if "sensor_depth" in batch else None
         mono_depth_gt = self.get_gt_img(batch["mono_depth"]) if "mono_depth" in batch else None

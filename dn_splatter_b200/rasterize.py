@@ -26,7 +26,7 @@ TILE = 16
 
 class _CapacityTracker:
     """Sync-free sizing of the intersection buffers: the count of every view is copied to pinned host memory
-    asynchronously; capacity for the next view = 1.3 x the largest count seen so far (rounded up).  A view whose
+    asynchronously; capacity for the next view = 1.15 x the largest count seen so far (rounded up).  A view whose
     count exceeded its capacity was rendered without its farthest intersections; `overflows` counts those."""
 
     SLOTS = 256
@@ -44,7 +44,7 @@ class _CapacityTracker:
         return self.seeds >= 2
 
     def capacity(self) -> int:
-        return int(self.max_seen * 1.3) + 4096
+        return int(self.max_seen * 1.15) + 4096
 
     def observe(self, n_isects_dev: Tensor, cap: int):
         if self.host is None:

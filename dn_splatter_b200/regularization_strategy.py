@@ -108,6 +108,46 @@ class _ScaleLoss(torch.autograd.Function):
         return g
 
 
+class FusedL1(torch.autograd.Function):
+    """mean |pred - gt| with gt fp32 or uint8 (/255): the parent SplatfactoModel's photometric L1 in one pass each way."""
+
+    @staticmethod
+    def forward(ctx, pred, gt):
+        lib = L.load()
+        if pred.device.type != "cuda" or gt.device != pred.device:
+            raise L.DnrError("FusedL1 needs CUDA tensors on one device (no CPU path)")
+        p = pred.detach().float().contiguous()
+        g = gt.detach().contiguous()
+        if g.dtype != torch.uint8:
+            g = g.float()
+        assert g.numel() == p.numel(), "pred / gt size mismatch"
+        out = torch.empty(1, dtype=torch.float32, device=p.device)
+        L.check(lib.dnr_l1_fwd(p.data_ptr(), g.data_ptr(), p.numel(), int(g.dtype == torch.uint8), out.data_ptr(), _stream()),
+                "dnr_l1_fwd")
+        ctx.keep = (p, g)
+        ctx.shape = pred.shape
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, v):
+        lib = L.load()
+        p, g = ctx.keep
+        v = v.detach().float().contiguous()
+        vp = torch.empty_like(p)
+        L.check(lib.dnr_l1_bwd(p.data_ptr(), g.data_ptr(), p.numel(), int(g.dtype == torch.uint8), v.data_ptr(), vp.data_ptr(),
+                               _stream()), "dnr_l1_bwd")
+        return vp.view(ctx.shape), None
+
+
+def u8_to_float(img: Tensor, divisor: float = 255.0, clamp_min: float = 0.0) -> Tensor:
+    """uint8 CUDA image -> fp32 (/divisor, clamped from below) in one kernel (get_gt_img + clamp of the reference)."""
+    src = img.contiguous()
+    dst = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    L.check(L.load().dnr_u8_to_f32(src.data_ptr(), src.numel(), float(divisor), float(clamp_min), dst.data_ptr(), _stream()),
+            "dnr_u8_to_f32")
+    return dst
+
+
 class RegularizationStrategy(nn.Module):
     """Depth and normal regularization super class (reference :99-118)."""
 

@@ -186,6 +186,15 @@ int dnr_loss_bwd(const DnrArgs* a, float* v_depth_out, float* v_normal_out, void
 int dnr_scale_loss_fwd(const float* scales, int32_t n_gauss, float* loss_out, void* stream);
 int dnr_scale_loss_bwd(const float* scales, int32_t n_gauss, const float* v_loss, float* v_scales, void* stream);
 
+/* Photometric L1 of the parent SplatfactoModel.get_loss_dict [EXT] (dn_splatter/dn_model.py:624-628 calls it):
+ * mean |pred - gt| over n floats; gt is fp32, or uint8 (gt_is_u8 != 0, scaled by 1/255 as get_gt_img does).
+ * fwd: *loss_out (zeroed by the call) = the mean.  bwd: v_pred[n] = (*v_loss or 1) * sign(pred - gt) / n. */
+int dnr_l1_fwd(const float* pred, const void* gt, int64_t n, int32_t gt_is_u8, float* loss_out, void* stream);
+int dnr_l1_bwd(const float* pred, const void* gt, int64_t n, int32_t gt_is_u8, const float* v_loss, float* v_pred,
+               void* stream);
+/* get_gt_img's uint8 -> float conversion in one pass: dst[i] = max(src[i] / divisor, clamp_min). */
+int dnr_u8_to_f32(const uint8_t* src, int64_t n, float divisor, float clamp_min, float* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -157,3 +157,24 @@ def test_dn_regularization_matches_reference_goldens(golden_dir):
                 torch.testing.assert_close(pd.grad, z["out_grad_pred_depth"], rtol=1e-4, atol=1e-8)
                 torch.testing.assert_close(pn.grad, z["out_grad_pred_normal"], rtol=1e-4, atol=1e-8)
                 torch.testing.assert_close(sc.grad, z["out_grad_scales"], rtol=1e-4, atol=1e-8)
+
+
+@needs_cuda
+def test_fused_l1_and_u8_conversion_match_torch():
+    from dn_splatter_b200.regularization_strategy import FusedL1, u8_to_float
+
+    g = torch.Generator().manual_seed(3)
+    pred = torch.rand(37, 53, 3, generator=g).cuda().requires_grad_(True)
+    gt8 = (torch.rand(37, 53, 3, generator=g) * 255).to(torch.uint8).cuda()
+    gtf = gt8.float() / 255.0
+    for gt in (gt8, gtf):
+        pred.grad = None
+        loss = FusedL1.apply(pred, gt)
+        (loss * 3.0).backward()
+        ref_p = pred.detach().clone().requires_grad_(True)
+        ref = (gtf - ref_p).abs().mean()
+        (ref * 3.0).backward()
+        torch.testing.assert_close(loss, ref, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(pred.grad, ref_p.grad, rtol=1e-6, atol=1e-9)
+    assert torch.equal(u8_to_float(gt8), gtf)
+    assert torch.equal(u8_to_float(gt8, 255.0, 10 / 255.0), gtf.clamp(min=10 / 255.0))

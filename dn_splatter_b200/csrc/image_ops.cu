@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256) scale_loss_bwd_kernel(const float* __rest
 
 template <bool U8>
 __device__ __forceinline__ float gt_at(const void* gt, int64_t i) {
-  return U8 ? (float)((const uint8_t*)gt)[i] / 255.0f : ((const float*)gt)[i];
+  return U8 ? (float)((const uint8_t*)gt)[i] * (1.0f / 255.0f) : ((const float*)gt)[i];
 }
 
 template <bool U8>
@@ -270,8 +270,9 @@ __global__ void __launch_bounds__(256) l1_bwd_kernel(const float* __restrict__ p
 
 __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ src, int64_t n, float divisor, float lo,
                                                        float* __restrict__ dst) {
+  const float inv = 1.0f / divisor;  // torch's CUDA `x / scalar` multiplies by the fp32 reciprocal: match it bit for bit
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    dst[i] = fmaxf((float)src[i] / divisor, lo);  // a true division, as image.float() / 255.0 in the reference
+    dst[i] = fmaxf((float)src[i] * inv, lo);
 }
 
 inline int stream_grid(int64_t n) {

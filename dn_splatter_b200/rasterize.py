@@ -44,7 +44,7 @@ class _CapacityTracker:
         return self.seeds >= 2
 
     def capacity(self) -> int:
-        return int(self.max_seen * 1.15) + 4096
+        return ((int(self.max_seen * 1.15) + 4096 + (1 << 21) - 1) >> 21) << 21  # 2M-entry steps: allocator-friendly
 
     def observe(self, n_isects_dev: Tensor, cap: int):
         if self.host is None:

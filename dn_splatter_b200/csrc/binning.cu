@@ -106,70 +106,138 @@ inline int tile_bits_for(int n_tiles) {
   return b;
 }
 
-// Pixel-centre rectangle of tile (tx,ty), clipped to the image.
-__device__ __forceinline__ bool tile_reachable(const DnrArgs& a, int g, float mx, float my, int tx, int ty) {
+// Per-Gaussian data of the precise-hit test, loaded one Gaussian per lane (32 independent load chains per warp)
+// and then broadcast lane by lane with shuffles while the whole warp walks that Gaussian's tile box.
+struct HitGauss {
+  int g, radius, x0, y0, nx, total;
+  float mx, my, A, B, C, boc, boa, lim;
+};
+
+__device__ __forceinline__ HitGauss load_hit_gauss(const DnrArgs& a, const int32_t* __restrict__ order, int i, int tiles_x,
+                                                   int tiles_y) {
+  HitGauss h;
+  h.g = 0; h.radius = 0; h.x0 = h.y0 = h.nx = h.total = 0;
+  h.mx = h.my = h.A = h.B = h.C = h.boc = h.boa = 0.f; h.lim = -1.f;
+  if (i < a.n_gauss) {
+    h.g = order[i];
+    h.radius = a.radii[h.g];
+    if (h.radius > 0) {
+      h.mx = a.means2d[h.g * 2 + 0]; h.my = a.means2d[h.g * 2 + 1];
+      int x1, y1;
+      dnr_tile_box(h.mx, h.my, h.radius, tiles_x, tiles_y, h.x0, h.y0, x1, y1);
+      h.nx = x1 - h.x0;
+      h.total = h.nx * (y1 - h.y0);
+      if (!(a.flags & DNR_FLAG_EXACT_LISTS)) {
+        h.A = a.conics[h.g * 3 + 0]; h.B = a.conics[h.g * 3 + 1]; h.C = a.conics[h.g * 3 + 2];
+        h.boc = h.B / h.C; h.boa = h.B / h.A;
+        h.lim = a.cull_lim[h.g];
+      }
+    }
+  }
+  return h;
+}
+
+__device__ __forceinline__ HitGauss bcast_hit_gauss(const HitGauss& h, int src) {
+  HitGauss o;
+  o.g = __shfl_sync(0xffffffffu, h.g, src); o.radius = __shfl_sync(0xffffffffu, h.radius, src);
+  o.x0 = __shfl_sync(0xffffffffu, h.x0, src); o.y0 = __shfl_sync(0xffffffffu, h.y0, src);
+  o.nx = __shfl_sync(0xffffffffu, h.nx, src); o.total = __shfl_sync(0xffffffffu, h.total, src);
+  o.mx = __shfl_sync(0xffffffffu, h.mx, src); o.my = __shfl_sync(0xffffffffu, h.my, src);
+  o.A = __shfl_sync(0xffffffffu, h.A, src); o.B = __shfl_sync(0xffffffffu, h.B, src); o.C = __shfl_sync(0xffffffffu, h.C, src);
+  o.boc = __shfl_sync(0xffffffffu, h.boc, src); o.boa = __shfl_sync(0xffffffffu, h.boa, src);
+  o.lim = __shfl_sync(0xffffffffu, h.lim, src);
+  return o;
+}
+
+// k-th tile (row-major) of the box; the float reciprocal is exact for the box sizes that occur (< 2^20 tiles)
+__device__ __forceinline__ void box_tile(const HitGauss& h, float inv_nx, int k, int& tx, int& ty) {
+  int row = (int)(((float)k + 0.5f) * inv_nx);
+  int col = k - row * h.nx;
+  if (col < 0) { --row; col += h.nx; }
+  if (col >= h.nx) { ++row; col -= h.nx; }
+  tx = h.x0 + col; ty = h.y0 + row;
+}
+
+__device__ __forceinline__ bool tile_hit(const DnrArgs& a, const HitGauss& h, int tx, int ty) {
   const float x0 = (float)(tx * DNR_TILE) + 0.5f, y0 = (float)(ty * DNR_TILE) + 0.5f;
   const float x1 = fminf((float)(tx * DNR_TILE + DNR_TILE - 1), (float)(a.width - 1)) + 0.5f;
   const float y1 = fminf((float)(ty * DNR_TILE + DNR_TILE - 1), (float)(a.height - 1)) + 0.5f;
-  return dnr_rect_hit(mx, my, a.conics[g * 3 + 0], a.conics[g * 3 + 1], a.conics[g * 3 + 2], a.cull_lim[g], x0, x1, y0, y1);
+  return dnr_rect_hit(h.mx, h.my, h.A, h.B, h.C, h.boc, h.boa, h.lim, x0, x1, y0, y1);
 }
 
-// One warp per depth-sorted Gaussian: number of tiles of its box that it can really reach.
+// One warp per 32 depth-sorted Gaussians: counts[i] = number of tiles of Gaussian i's box that it can really reach.
 __global__ void __launch_bounds__(256) count_kernel(const DnrArgs a, const int32_t* __restrict__ order,
                                                    int32_t* __restrict__ counts, int tiles_x, int tiles_y) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp > a.n_gauss) return;
-  if (warp == a.n_gauss) { if (lane == 0) counts[warp] = 0; return; }
-  const int g = order[warp];
-  const int radius = a.radii[g];
-  if (radius <= 0) { if (lane == 0) counts[warp] = 0; return; }
-  if (a.flags & DNR_FLAG_EXACT_LISTS) { if (lane == 0) counts[warp] = a.tiles_per_gauss[g]; return; }
-  const float mx = a.means2d[g * 2 + 0], my = a.means2d[g * 2 + 1];
-  int x0, y0, x1, y1;
-  dnr_tile_box(mx, my, radius, tiles_x, tiles_y, x0, y0, x1, y1);
-  const int nx = x1 - x0, total = nx * (y1 - y0);
-  int cnt = 0;
-  for (int k = lane; k < total; k += 32) cnt += tile_reachable(a, g, mx, my, x0 + k % nx, y0 + k / nx) ? 1 : 0;
+  const int base = warp * 32;
+  if (base > a.n_gauss) return;
+  const HitGauss mine = load_hit_gauss(a, order, base + lane, tiles_x, tiles_y);
+  const bool exact = (a.flags & DNR_FLAG_EXACT_LISTS) != 0;
+  int my_count = exact ? mine.total : 0;
+  if (!exact) {
+    unsigned todo = __ballot_sync(0xffffffffu, mine.total > 0);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const HitGauss h = bcast_hit_gauss(mine, src);
+      const float inv_nx = 1.0f / (float)h.nx;
+      int cnt = 0;
+      for (int k = lane; k < h.total; k += 32) {
+        int tx, ty;
+        box_tile(h, inv_nx, k, tx, ty);
+        cnt += tile_hit(a, h, tx, ty) ? 1 : 0;
+      }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0) counts[warp] = cnt;
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (lane == src) my_count = cnt;
+    }
+  }
+  if (base + lane <= a.n_gauss) counts[base + lane] = (base + lane < a.n_gauss) ? my_count : 0;
 }
 
-// One warp per depth-sorted Gaussian; lanes stride over its tile box (row-major, as gsplat emits), survivors
-// are ballot-compacted so the row-major order is kept.  Entries past the capacity are dropped (the caller sees
-// n_isects_dev > capacity and retries).
+// One warp per 32 depth-sorted Gaussians; for each, lanes stride over its tile box (row-major, as gsplat emits),
+// survivors are ballot-compacted so the row-major order is kept.  Entries past the capacity are dropped (the caller
+// sees n_isects_dev > capacity and retries).
 template <typename KeyT>
 __global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_t* __restrict__ order,
                                                   const int64_t* __restrict__ isect_start, KeyT* __restrict__ keys,
                                                   int32_t* __restrict__ gids, int tiles_x, int tiles_y) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= a.n_gauss) return;
-  const int64_t start = isect_start[warp];
-  const int count = (int)(isect_start[warp + 1] - start);
-  if (count == 0) return;
+  const int base = warp * 32;
+  if (base >= a.n_gauss) return;
+  const HitGauss mine = load_hit_gauss(a, order, base + lane, tiles_x, tiles_y);
+  const int64_t my_start = (base + lane < a.n_gauss) ? isect_start[base + lane] : 0;
+  const int64_t my_end = (base + lane < a.n_gauss) ? isect_start[base + lane + 1] : 0;
   const int64_t cap = a.n_isects;
-  const int g = order[warp];
-  const float mx = a.means2d[g * 2 + 0], my = a.means2d[g * 2 + 1];
-  int x0, y0, x1, y1;
-  dnr_tile_box(mx, my, a.radii[g], tiles_x, tiles_y, x0, y0, x1, y1);
-  const int nx = x1 - x0, total = nx * (y1 - y0);
   const bool exact = (a.flags & DNR_FLAG_EXACT_LISTS) != 0;
-  int written = 0;
-  for (int k0 = 0; k0 < total; k0 += 32) {
-    const int k = k0 + lane;
-    const int ty = y0 + k / nx, tx = x0 + k % nx;
-    const bool hit = (k < total) && (exact || tile_reachable(a, g, mx, my, tx, ty));
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (hit) {
-      const int64_t dst = start + written + __popc(m & ((1u << lane) - 1u));
-      if (dst < cap) {
-        keys[dst] = (KeyT)(ty * tiles_x + tx);
-        gids[dst] = g;
+  unsigned todo = __ballot_sync(0xffffffffu, my_end > my_start);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const HitGauss h = bcast_hit_gauss(mine, src);
+    const int64_t start = __shfl_sync(0xffffffffu, my_start, src);
+    const float inv_nx = 1.0f / (float)h.nx;
+    int written = 0;
+    for (int k0 = 0; k0 < h.total; k0 += 32) {
+      const int k = k0 + lane;
+      int tx = 0, ty = 0;
+      bool hit = false;
+      if (k < h.total) {
+        box_tile(h, inv_nx, k, tx, ty);
+        hit = exact || tile_hit(a, h, tx, ty);
       }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int64_t dst = start + written + __popc(m & ((1u << lane) - 1u));
+        if (dst < cap) {
+          keys[dst] = (KeyT)(ty * tiles_x + tx);
+          gids[dst] = h.g;
+        }
+      }
+      written += __popc(m);
     }
-    written += __popc(m);
   }
 }
 
@@ -213,7 +281,7 @@ int bin_sort_impl(const DnrArgs* a, cudaStream_t s, int n_tiles, int tile_bits) 
   const int64_t cap = a->n_isects;
   SortWs<KeyT> w = carve_sort<KeyT>(a->ws_sort, cap, tile_bits);
   if (cap > 0) {
-    const int64_t threads = (int64_t)a->n_gauss * 32;
+    const int64_t threads = (((int64_t)a->n_gauss + 31) / 32) * 32;  // one warp per 32 Gaussians
     emit_kernel<KeyT><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(*a, sw.order, sw.isect_start, w.keys_in, w.gids_in,
                                                                           tiles_x, tiles_y);
     DNR_CHECK_LAUNCH();
@@ -251,7 +319,7 @@ extern "C" int dnr_bin_scan(const DnrArgs* a, void* stream, int64_t* n_isects_ho
   DNR_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, bytes, (const uint32_t*)a->depth_keys, w.keys_sorted,
                                            (const int32_t*)w.iota, w.order, n, 0, 32, s));
   {
-    const int64_t threads = ((int64_t)n + 1) * 32;
+    const int64_t threads = ((int64_t)n / 32 + 1) * 32;  // one warp per 32 Gaussians (+ the terminating zero)
     count_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(*a, w.order, w.counts, dnr_tiles_x(a), dnr_tiles_y(a));
     DNR_CHECK_LAUNCH();
   }

@@ -371,8 +371,12 @@ __global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(const DnrArgs a
   const bool visible = radius > 0;
   s_vis[threadIdx.x] = visible ? 1 : 0;
   float* srow = s_rest + threadIdx.x * PB_REST_MAX;
+  // visible rows are fully written by the SH section below; invisible rows are only read by the dense-overwrite path
+  if (!visible && !acc) {
 #pragma unroll
-  for (int k = 0; k < PB_REST_MAX; ++k) srow[k] = 0.f;
+    for (int k = 0; k < PB_REST_MAX; ++k) srow[k] = 0.f;
+  }
+  if (acc && !__syncthreads_or(visible ? 1 : 0)) return;  // nothing to accumulate from this CTA
   float vm[3] = {0, 0, 0}, vq[4] = {0, 0, 0, 0}, vs[3] = {0, 0, 0}, vo = 0.f, vdc[3] = {0, 0, 0};
   if (in_range && !visible && !acc) {
     for (int k = 0; k < 3; ++k) { a.v_means[i * 3 + k] = 0.f; a.v_scales[i * 3 + k] = 0.f; a.v_sh_dc[i * 3 + k] = 0.f; }

@@ -188,6 +188,7 @@ class _DnRasterize(torch.autograd.Function):
     def forward(ctx, means, quats, scales, opacities, sh_dc, sh_rest, viewmat, K, c2w, settings: RasterSettings, holder: dict):
         lib = L.load()
         s = settings
+        ctx.set_materialize_grads(False)  # unused output gradients arrive as None instead of freshly filled zero tensors
         dev = _require_cuda(means, quats, scales, opacities, sh_dc, sh_rest)
         # camera on the host (CPU tensors) -> passed by value, no device traffic; on the device -> read by the kernels
         host_cam = None

@@ -279,30 +279,36 @@ def main():
     losses = []
     copy_stream = torch.cuda.Stream(device=device)
     loss_host = torch.zeros(64, dtype=torch.float32).pin_memory()
-    state = {"next": None, "pending": []}
+    NBUF = 3  # device staging buffers (allocated once: no allocator traffic, no cross-stream frees in the timed region)
+    stage = [{k: torch.empty_like(v, device=device) for k, v in pin_sets[0].items()} for _ in range(NBUF)]
+    ready = [torch.cuda.Event() for _ in range(NBUF)]     # H2D of the slot finished (recorded on the copy stream)
+    consumed = [torch.cuda.Event() for _ in range(NBUF)]  # compute that read the slot finished (compute stream)
+    state = {"prefetched": -1, "pending": []}
 
     def prefetch(s):
         """H2D of step s's supervision maps on the copy stream (overlaps the previous step's compute)."""
+        slot = s % NBUF
         with torch.cuda.stream(copy_stream):
-            b = {k: v.to(device, non_blocking=True) for k, v in pin_sets[s % len(pin_sets)].items()}
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return b, ev
+            copy_stream.wait_event(consumed[slot])  # the step that last used this slot has finished reading it
+            for k, v in pin_sets[s % len(pin_sets)].items():
+                stage[slot][k].copy_(v, non_blocking=True)
+            ready[slot].record(copy_stream)
+        state["prefetched"] = s
 
     def e2e_step(s):
-        if state["next"] is None:
-            state["next"] = prefetch(s)
-        b, ev = state["next"]
-        torch.cuda.current_stream().wait_event(ev)
-        for t in b.values():
-            t.record_stream(torch.cuda.current_stream())
-        state["next"] = prefetch(s + 1)
-        loss = run_step(model, bucket, cams[my_views[s % len(my_views)]], b)
-        slot = s % 64
-        loss_host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)  # D2H read of the step's result
+        if state["prefetched"] < s:
+            prefetch(s)
+        slot = s % NBUF
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready[slot])
+        prefetch(s + 1)
+        loss = run_step(model, bucket, cams[my_views[s % len(my_views)]], stage[slot])
+        consumed[slot].record(cur)
+        ls = s % 64
+        loss_host[ls:ls + 1].copy_(loss.detach().reshape(1), non_blocking=True)  # D2H read of the step's result
         rev = torch.cuda.Event()
         rev.record()
-        state["pending"].append((slot, rev))
+        state["pending"].append((ls, rev))
         while len(state["pending"]) > 2:  # consume results at most 2 steps late
             sl, e = state["pending"].pop(0)
             e.synchronize()
@@ -313,7 +319,7 @@ def main():
             e.synchronize()
             losses.append(float(loss_host[sl]))
         state["pending"] = []
-        state["next"] = None
+        state["prefetched"] = -1
 
     # untimed setup: visit every view of this rank once (camera caches, intersection-capacity statistics) — a training
     # run revisits each view thousands of times; then the warm-up steps, then the timed device-resident run

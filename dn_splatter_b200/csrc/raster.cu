@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256 / PPT) raster_bwd_kernel(const DnrArgs a, 
   // ---- range actually composited by this tile ----
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
-  if (lane == 0) red_last[warp] = wl;
+  if (lane == 0) red_last[warp] = wl;  // wl: deepest record any pixel of this warp composited
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(256 / PPT) raster_bwd_kernel(const DnrArgs a, 
     const int chi = hi - c * CH;
     const int n_c = min(CH, chi - start);
     const float4* r4 = reinterpret_cast<const float4*>(recs[stage]);
-    for (int t = 0; t < n_c; ++t) {
+    // records deeper than anything this warp composited are skipped without touching them (warp-uniform)
+    for (int t = max(0, chi - 1 - wl); t < n_c; ++t) {
       const int idx = chi - 1 - t;
       const float4 q0 = r4[t * (REC / 4) + 0];
       const float4 q1 = r4[t * (REC / 4) + 1];

@@ -357,7 +357,7 @@ constexpr int PB_REST_MAX = 45;    // (16 - 1) * 3 floats of higher-order SH gra
 // The 180 B/Gaussian SH-gradient rows are staged in shared memory (stride 45 words: conflict-free) and written
 // by the whole CTA as one contiguous, coalesced stream instead of 45 strided 4-byte stores per thread.
 template <bool NORMALS>
-__global__ void __launch_bounds__(PB_THREADS) project_bwd_kernel(const DnrArgs a) {
+__global__ void __launch_bounds__(PB_THREADS, 8) project_bwd_kernel(const DnrArgs a) {
   __shared__ float s_rest[PB_THREADS * PB_REST_MAX];
   __shared__ unsigned char s_vis[PB_THREADS];
   __shared__ unsigned char s_list[PB_THREADS];

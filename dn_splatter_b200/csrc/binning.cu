@@ -106,18 +106,24 @@ inline int tile_bits_for(int n_tiles) {
   return b;
 }
 
-// Per-Gaussian data of the precise-hit test, loaded one Gaussian per lane (32 independent load chains per warp)
-// and then broadcast lane by lane with shuffles while the whole warp walks that Gaussian's tile box.
+// ---- precise-hit emission -------------------------------------------------------------------------------------
+// For a Gaussian (centre m, conic A,B,C) and the largest sigma `lim` at which a pixel can still reach alpha >= 1/255,
+// the reachable region is the ellipse q(e) = 0.5 (A ex^2 + C ey^2) + B ex ey <= lim (e = pixel - m).  For one row of
+// tiles (pixel centres ey in [e0,e1]) the ellipse slice is convex, so the tiles it touches form ONE span: those
+// whose centre range overlaps [xmin,xmax], the x-extent of the slice.  With D(ey) = (B^2-AC) ey^2 + 2 A lim the
+// slice at height ey is ex in [(-B ey -+ sqrt D)/A]; the upper root is concave in ey (max at the ellipse's right-most
+// point or at an end of the interval), the lower root convex.  Everything is widened by small slacks: the span may
+// only err on the keeping side (kept-but-unreachable pairs are skipped per pixel anyway; images are bit-identical).
 struct HitGauss {
-  int g, radius, x0, y0, nx, total;
-  float mx, my, A, B, C, boc, boa, lim;
+  int g, radius, x0, y0, nx, ny;
+  float mx, my, A, B, invA, bac, twoAL, ex_max, ey_max, ey_star;
 };
 
 __device__ __forceinline__ HitGauss load_hit_gauss(const DnrArgs& a, const int32_t* __restrict__ order, int i, int tiles_x,
                                                    int tiles_y) {
   HitGauss h;
-  h.g = 0; h.radius = 0; h.x0 = h.y0 = h.nx = h.total = 0;
-  h.mx = h.my = h.A = h.B = h.C = h.boc = h.boa = 0.f; h.lim = -1.f;
+  h.g = 0; h.radius = 0; h.x0 = h.y0 = h.nx = h.ny = 0;
+  h.mx = h.my = h.A = h.B = h.invA = h.bac = h.twoAL = h.ex_max = h.ey_max = h.ey_star = 0.f;
   if (i < a.n_gauss) {
     h.g = order[i];
     h.radius = a.radii[h.g];
@@ -126,11 +132,19 @@ __device__ __forceinline__ HitGauss load_hit_gauss(const DnrArgs& a, const int32
       int x1, y1;
       dnr_tile_box(h.mx, h.my, h.radius, tiles_x, tiles_y, h.x0, h.y0, x1, y1);
       h.nx = x1 - h.x0;
-      h.total = h.nx * (y1 - h.y0);
+      h.ny = y1 - h.y0;
       if (!(a.flags & DNR_FLAG_EXACT_LISTS)) {
-        h.A = a.conics[h.g * 3 + 0]; h.B = a.conics[h.g * 3 + 1]; h.C = a.conics[h.g * 3 + 2];
-        h.boc = h.B / h.C; h.boa = h.B / h.A;
-        h.lim = a.cull_lim[h.g];
+        const float A = a.conics[h.g * 3 + 0], B = a.conics[h.g * 3 + 1], C = a.conics[h.g * 3 + 2];
+        const float L = a.cull_lim[h.g];
+        const float det = A * C - B * B;
+        if (!(L > 0.f) || !(det > 0.f)) {
+          h.ny = 0;  // cannot reach alpha >= 1/255 anywhere
+        } else {
+          h.A = A; h.B = B; h.invA = 1.0f / A; h.bac = -det; h.twoAL = 2.0f * A * L;
+          h.ex_max = sqrtf(2.0f * L * C / det) * 1.0001f + 0.01f;
+          h.ey_max = sqrtf(2.0f * L * A / det) * 1.0001f + 0.01f;
+          h.ey_star = -B * h.ex_max / C;  // height of the right-most point; the left-most one sits at -ey_star
+        }
       }
     }
   }
@@ -141,64 +155,55 @@ __device__ __forceinline__ HitGauss bcast_hit_gauss(const HitGauss& h, int src) 
   HitGauss o;
   o.g = __shfl_sync(0xffffffffu, h.g, src); o.radius = __shfl_sync(0xffffffffu, h.radius, src);
   o.x0 = __shfl_sync(0xffffffffu, h.x0, src); o.y0 = __shfl_sync(0xffffffffu, h.y0, src);
-  o.nx = __shfl_sync(0xffffffffu, h.nx, src); o.total = __shfl_sync(0xffffffffu, h.total, src);
+  o.nx = __shfl_sync(0xffffffffu, h.nx, src); o.ny = __shfl_sync(0xffffffffu, h.ny, src);
   o.mx = __shfl_sync(0xffffffffu, h.mx, src); o.my = __shfl_sync(0xffffffffu, h.my, src);
-  o.A = __shfl_sync(0xffffffffu, h.A, src); o.B = __shfl_sync(0xffffffffu, h.B, src); o.C = __shfl_sync(0xffffffffu, h.C, src);
-  o.boc = __shfl_sync(0xffffffffu, h.boc, src); o.boa = __shfl_sync(0xffffffffu, h.boa, src);
-  o.lim = __shfl_sync(0xffffffffu, h.lim, src);
+  o.A = __shfl_sync(0xffffffffu, h.A, src); o.B = __shfl_sync(0xffffffffu, h.B, src);
+  o.invA = __shfl_sync(0xffffffffu, h.invA, src); o.bac = __shfl_sync(0xffffffffu, h.bac, src);
+  o.twoAL = __shfl_sync(0xffffffffu, h.twoAL, src); o.ex_max = __shfl_sync(0xffffffffu, h.ex_max, src);
+  o.ey_max = __shfl_sync(0xffffffffu, h.ey_max, src); o.ey_star = __shfl_sync(0xffffffffu, h.ey_star, src);
   return o;
 }
 
-// k-th tile (row-major) of the box; the float reciprocal is exact for the box sizes that occur (< 2^20 tiles)
-__device__ __forceinline__ void box_tile(const HitGauss& h, float inv_nx, int k, int& tx, int& ty) {
-  int row = (int)(((float)k + 0.5f) * inv_nx);
-  int col = k - row * h.nx;
-  if (col < 0) { --row; col += h.nx; }
-  if (col >= h.nx) { ++row; col -= h.nx; }
-  tx = h.x0 + col; ty = h.y0 + row;
+// Tiles [lo, hi) of tile-row `ty` that the Gaussian can reach (empty when hi <= lo); `exact` keeps the whole box row.
+__device__ __forceinline__ void row_span(const HitGauss& h, int ty, bool exact, int& lo, int& hi) {
+  lo = h.x0; hi = h.x0 + h.nx;
+  if (exact) return;
+  float e0 = ((float)(ty * DNR_TILE) + 0.5f) - h.my - 0.01f;
+  float e1 = ((float)(ty * DNR_TILE + DNR_TILE - 1) + 0.5f) - h.my + 0.01f;
+  if (e0 > h.ey_max || e1 < -h.ey_max) { hi = lo; return; }
+  e0 = fmaxf(e0, -h.ey_max); e1 = fminf(e1, h.ey_max);
+  const float s0 = sqrtf(fmaxf(fmaf(h.bac, e0 * e0, h.twoAL), 0.f)), s1 = sqrtf(fmaxf(fmaf(h.bac, e1 * e1, h.twoAL), 0.f));
+  float xmax = fmaxf((-h.B * e0 + s0) * h.invA, (-h.B * e1 + s1) * h.invA);
+  float xmin = fminf((-h.B * e0 - s0) * h.invA, (-h.B * e1 - s1) * h.invA);
+  if (h.ey_star >= e0 && h.ey_star <= e1) xmax = h.ex_max;
+  if (-h.ey_star >= e0 && -h.ey_star <= e1) xmin = -h.ex_max;
+  xmax = xmax + 0.01f + 1e-5f * fabsf(xmax);
+  xmin = xmin - 0.01f - 1e-5f * fabsf(xmin);
+  // tile tx holds pixel centres [16 tx + 0.5, 16 tx + 15.5]
+  const int t_lo = (int)ceilf((h.mx + xmin - 15.5f) * (1.0f / DNR_TILE));
+  const int t_hi = (int)floorf((h.mx + xmax - 0.5f) * (1.0f / DNR_TILE)) + 1;
+  lo = max(lo, t_lo); hi = min(hi, t_hi);
 }
 
-__device__ __forceinline__ bool tile_hit(const DnrArgs& a, const HitGauss& h, int tx, int ty) {
-  const float x0 = (float)(tx * DNR_TILE) + 0.5f, y0 = (float)(ty * DNR_TILE) + 0.5f;
-  const float x1 = fminf((float)(tx * DNR_TILE + DNR_TILE - 1), (float)(a.width - 1)) + 0.5f;
-  const float y1 = fminf((float)(ty * DNR_TILE + DNR_TILE - 1), (float)(a.height - 1)) + 0.5f;
-  return dnr_rect_hit(h.mx, h.my, h.A, h.B, h.C, h.boc, h.boa, h.lim, x0, x1, y0, y1);
-}
-
-// One warp per 32 depth-sorted Gaussians: counts[i] = number of tiles of Gaussian i's box that it can really reach.
+// One lane per depth-sorted Gaussian: counts[i] = number of tiles of its box that it can really reach.
 __global__ void __launch_bounds__(256) count_kernel(const DnrArgs a, const int32_t* __restrict__ order,
                                                    int32_t* __restrict__ counts, int tiles_x, int tiles_y) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int base = warp * 32;
-  if (base > a.n_gauss) return;
-  const HitGauss mine = load_hit_gauss(a, order, base + lane, tiles_x, tiles_y);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > a.n_gauss) return;
+  const HitGauss h = load_hit_gauss(a, order, i, tiles_x, tiles_y);
   const bool exact = (a.flags & DNR_FLAG_EXACT_LISTS) != 0;
-  int my_count = exact ? mine.total : 0;
-  if (!exact) {
-    unsigned todo = __ballot_sync(0xffffffffu, mine.total > 0);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const HitGauss h = bcast_hit_gauss(mine, src);
-      const float inv_nx = 1.0f / (float)h.nx;
-      int cnt = 0;
-      for (int k = lane; k < h.total; k += 32) {
-        int tx, ty;
-        box_tile(h, inv_nx, k, tx, ty);
-        cnt += tile_hit(a, h, tx, ty) ? 1 : 0;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      if (lane == src) my_count = cnt;
-    }
+  int cnt = 0;
+  for (int r = 0; r < h.ny; ++r) {
+    int lo, hi;
+    row_span(h, h.y0 + r, exact, lo, hi);
+    cnt += max(hi - lo, 0);
   }
-  if (base + lane <= a.n_gauss) counts[base + lane] = (base + lane < a.n_gauss) ? my_count : 0;
+  counts[i] = (i < a.n_gauss) ? cnt : 0;
 }
 
-// One warp per 32 depth-sorted Gaussians; for each, lanes stride over its tile box (row-major, as gsplat emits),
-// survivors are ballot-compacted so the row-major order is kept.  Entries past the capacity are dropped (the caller
-// sees n_isects_dev > capacity and retries).
+// One warp per 32 depth-sorted Gaussians; for each Gaussian the lanes take its tile rows, compute the row spans, scan
+// their lengths and write the spans (row-major, ascending x: the order gsplat emits).  Entries past the capacity are
+// dropped (the caller sees n_isects_dev > capacity and retries).
 template <typename KeyT>
 __global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_t* __restrict__ order,
                                                   const int64_t* __restrict__ isect_start, KeyT* __restrict__ keys,
@@ -217,26 +222,27 @@ __global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_
     const int src = __ffs(todo) - 1;
     todo &= todo - 1;
     const HitGauss h = bcast_hit_gauss(mine, src);
-    const int64_t start = __shfl_sync(0xffffffffu, my_start, src);
-    const float inv_nx = 1.0f / (float)h.nx;
-    int written = 0;
-    for (int k0 = 0; k0 < h.total; k0 += 32) {
-      const int k = k0 + lane;
-      int tx = 0, ty = 0;
-      bool hit = false;
-      if (k < h.total) {
-        box_tile(h, inv_nx, k, tx, ty);
-        hit = exact || tile_hit(a, h, tx, ty);
+    int64_t dst0 = __shfl_sync(0xffffffffu, my_start, src);
+    for (int r0 = 0; r0 < h.ny; r0 += 32) {
+      const int r = r0 + lane;
+      int lo = 0, hi = 0;
+      if (r < h.ny) row_span(h, h.y0 + r, exact, lo, hi);
+      const int len = max(hi - lo, 0);
+      int incl = len;  // inclusive warp scan of the span lengths
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
       }
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        const int64_t dst = start + written + __popc(m & ((1u << lane) - 1u));
-        if (dst < cap) {
-          keys[dst] = (KeyT)(ty * tiles_x + tx);
-          gids[dst] = h.g;
+      const int64_t dst = dst0 + (incl - len);
+      const int row_key = (h.y0 + r) * tiles_x;
+      for (int k = 0; k < len; ++k) {
+        if (dst + k < cap) {
+          keys[dst + k] = (KeyT)(row_key + lo + k);
+          gids[dst + k] = h.g;
         }
       }
-      written += __popc(m);
+      dst0 += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
 }
@@ -319,7 +325,7 @@ extern "C" int dnr_bin_scan(const DnrArgs* a, void* stream, int64_t* n_isects_ho
   DNR_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, bytes, (const uint32_t*)a->depth_keys, w.keys_sorted,
                                            (const int32_t*)w.iota, w.order, n, 0, 32, s));
   {
-    const int64_t threads = ((int64_t)n / 32 + 1) * 32;  // one warp per 32 Gaussians (+ the terminating zero)
+    const int64_t threads = (int64_t)n + 1;  // one lane per Gaussian (+ the terminating zero)
     count_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(*a, w.order, w.counts, dnr_tiles_x(a), dnr_tiles_y(a));
     DNR_CHECK_LAUNCH();
   }

@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--cpu-crop", default="256x144")
     ap.add_argument("--sync", action="store_true", help="read the intersection count back every view (host sync)")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph captured step")
     return ap.parse_args()
 
 
@@ -291,14 +292,28 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    graphed = None
+
     def resident_step(s):
-        run_step(model, bucket, cams[my_views[s % len(my_views)]], dev_sets[s % len(dev_sets)])
+        cam = cams[my_views[s % len(my_views)]]
+        if graphed is None:
+            run_step(model, bucket, cam, dev_sets[s % len(dev_sets)])
+        else:  # supervision maps: device-resident set -> the graph's static buffers (D2D), then ONE graph launch
+            for k, v in dev_sets[s % len(dev_sets)].items():
+                graphed.batches[0][k].copy_(v, non_blocking=True)
+            graphed(cam, 0)
+            bucket.all_reduce()
 
     losses = []
     copy_stream = torch.cuda.Stream(device=device)
     loss_host = torch.zeros(64, dtype=torch.float32).pin_memory()
     NBUF = 3  # device staging buffers (allocated once: no allocator traffic, no cross-stream frees in the timed region)
     stage = [{k: torch.empty_like(v, device=device) for k, v in pin_sets[0].items()} for _ in range(NBUF)]
+
+    def use_graph_buffers():
+        nonlocal NBUF, stage
+        NBUF, stage = len(graphed.batches), graphed.batches  # H2D straight into the graph's static buffers
+
     ready = [torch.cuda.Event() for _ in range(NBUF)]     # H2D of the slot finished (recorded on the copy stream)
     consumed = [torch.cuda.Event() for _ in range(NBUF)]  # compute that read the slot finished (compute stream)
     state = {"prefetched": -1, "pending": []}
@@ -320,7 +335,12 @@ def main():
         cur = torch.cuda.current_stream()
         cur.wait_event(ready[slot])
         prefetch(s + 1)
-        loss = run_step(model, bucket, cams[my_views[s % len(my_views)]], stage[slot])
+        cam = cams[my_views[s % len(my_views)]]
+        if graphed is None:
+            loss = run_step(model, bucket, cam, stage[slot])
+        else:
+            loss = graphed(cam, slot)
+            bucket.all_reduce()
         consumed[slot].record(cur)
         ls = s % 64
         loss_host[ls:ls + 1].copy_(loss.detach().reshape(1), non_blocking=True)  # D2H read of the step's result
@@ -346,6 +366,18 @@ def main():
             model.get_outputs(cams[v])
     for s in range(max(3, args.warmup)):
         resident_step(s)
+    launches_per_step = None
+    if not args.no_graph:
+        from dn_splatter_b200 import _lib as _L0
+        from dn_splatter_b200.graph_step import GraphedTrainStep
+
+        l0 = dict(_L0.LAUNCHES)
+        graphed = GraphedTrainStep(model, bucket, cams[my_views[0]], dev_sets[0], n_slots=3, warmup=2)
+        n_eager = 2 + 3  # warm-up calls + one capture per slot
+        launches_per_step = {k: (_L0.LAUNCHES[k] - l0[k]) // n_eager for k in l0}
+        use_graph_buffers()
+        for s in range(3):
+            resident_step(s)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -354,6 +386,8 @@ def main():
     launches0 = dict(_L.LAUNCHES)
     ms = timed(args.steps, resident_step)
     launches = {k: _L.LAUNCHES[k] - launches0[k] for k in launches0}
+    if launches_per_step is not None:  # graph replays re-issue the launches recorded at capture
+        launches = {k: v * args.steps for k, v in launches_per_step.items()}
     clocks = sampler.stop() if rank == 0 else None
     pix = args.width * args.height
     value = world * args.steps * pix / 1e6 / (ms / 1e3)
@@ -375,6 +409,8 @@ def main():
 
     # per-stage device times (CUDA events on the launching stream) for the roofline of the dominant kernel
     stages, roof = {}, None
+    graph_info = None if graphed is None else {"capacity": graphed.capacity, "slots": len(graphed.graphs)}
+    graphed = None  # the instrumented pass below runs eagerly
     if rank == 0:
         R.STAGE_EVENTS = []
         n_prof = min(args.steps, 10)
@@ -432,6 +468,7 @@ def main():
             "gpu_launches_note": f"hand-written dnr kernels counted at the C-ABI calls of the timed region; the same calls ran "
                                  f"{launches['cub']} cub radix-sort/scan passes (compiled into libdnr_b200.so)",
             "roofline": roof, "stages_ms": stages, "cpu_baseline": cpu, "last_loss": losses[-1] if losses else None,
+            "cuda_graph": graph_info, "isect_capacity_report": {str(k): v for k, v in R.capacity_report().items()},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -378,6 +378,10 @@ class DNSplatterModel(torch.nn.Module):
             cache[scale_fac] = (camera.get_intrinsics_matrices()[0].float().cpu(), int(camera.width.flatten()[0]),
                                 int(camera.height.flatten()[0]), c2w_host, get_viewmat(c2w_host))
         K, W, H, c2w_fixed, viewmat = cache[scale_fac]
+        fixed_capacity = 0
+        gc = self.__dict__.get("_graph_cam")
+        if gc is not None:  # CUDA-graph mode: camera in static device buffers (refreshed before each replay), fixed capacity
+            K, c2w_fixed, viewmat, fixed_capacity = gc["K"], gc["c2w"], gc["viewmat"], gc["capacity"]
         self.last_size = (H, W)
         camera.rescale_output_resolution(scale_fac)
         sh_degree_to_use = min(self.step // cfg.sh_degree_interval, cfg.sh_degree)
@@ -389,7 +393,7 @@ class DNSplatterModel(torch.nn.Module):
             background=background, render_normals=cfg.predict_normals,
             c2w=c2w_fixed,
             grad_sink=self._bucket.sink() if (self._bucket is not None and torch.is_grad_enabled()) else None,
-            exact_lists=cfg.exact_isect_lists, sync_free=cfg.sync_free,
+            exact_lists=cfg.exact_isect_lists, sync_free=cfg.sync_free, fixed_capacity=fixed_capacity,
         )
         self.raster_out = out
         self.xys = out.means2d[None]  # [1,N,2]; .grad / .absgrad live on out.means2d after backward

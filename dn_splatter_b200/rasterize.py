@@ -76,6 +76,17 @@ class _CapacityTracker:
 _CAPACITY: dict = {}
 
 
+def suggested_capacity(n_gauss: int, width: int, height: int, render_normals: bool = True, exact_lists: bool = False,
+                       device_index: Optional[int] = None) -> int:
+    """Capacity (1.15 x the largest intersection count seen in sync-free mode, 2M-rounded) for graph capture."""
+    best = 0
+    for (di, n, w, h, rn, ex), t in _CAPACITY.items():
+        if (n, w, h, rn, ex) == (n_gauss, width, height, render_normals, exact_lists) and (device_index in (None, di)):
+            t.drain(wait=True)
+            best = max(best, t.capacity())
+    return best
+
+
 def capacity_report() -> dict:
     """{key: (max intersections seen, truncated views)} for the sync-free mode; waits for pending counts."""
     out = {}
@@ -116,6 +127,7 @@ class RasterSettings:
     surface_normal: bool = True
     exact_lists: bool = False  # parity mode: gsplat's full bbox intersection lists instead of the precise-hit lists
     sync_free: bool = False  # size the intersection buffers from past views instead of reading the count back
+    fixed_capacity: int = 0  # > 0: use exactly this many intersection slots, no host bookkeeping (CUDA-graph capture)
 
 
 class RasterOutput(NamedTuple):
@@ -249,7 +261,11 @@ class _DnRasterize(torch.autograd.Function):
         _set(a, ws_scan=ws_scan)
         cap_key = (dev.index, n, W, H, s.render_normals, s.exact_lists)
         tracker = _CAPACITY.get(cap_key) if s.sync_free else None
-        if tracker is not None and tracker.ready():
+        if s.fixed_capacity > 0:
+            # graph-capturable: no read-back, no events, no host state; a view needing more slots is truncated
+            L.check(_timed("bin_scan", lib.dnr_bin_scan, C.byref(a), st, None), "dnr_bin_scan")
+            n_isects = int(s.fixed_capacity)
+        elif tracker is not None and tracker.ready():
             # sync-free: nothing is read back on this stream; capacity comes from the counts of earlier views
             L.check(_timed("bin_scan", lib.dnr_bin_scan, C.byref(a), st, None), "dnr_bin_scan")
             n_isects = tracker.capacity()
@@ -358,7 +374,7 @@ def dn_rasterize(
     far_plane: float = 1e10, eps2d: float = 0.3, antialiased: bool = False,
     background: Sequence[float] = (0.0, 0.0, 0.0), render_normals: bool = True, c2w: Optional[Tensor] = None,
     activated: bool = False, surface_normal: bool = True, grad_sink: Optional[dict] = None,
-    exact_lists: bool = False, sync_free: bool = False,
+    exact_lists: bool = False, sync_free: bool = False, fixed_capacity: int = 0,
 ) -> RasterOutput:
     """Renders one view.  Inputs are the reference's RAW gauss_params (log-scales, opacity logits,
     un-normalised wxyz quats, SH coefficients split as features_dc / features_rest) unless
@@ -370,7 +386,7 @@ def dn_rasterize(
     settings = RasterSettings(width=int(width), height=int(height), sh_degree=int(sh_degree), near_plane=near_plane,
                               far_plane=far_plane, eps2d=eps2d, antialiased=antialiased, render_normals=render_normals,
                               activated=activated, background=bg, surface_normal=surface_normal, exact_lists=exact_lists,
-                              sync_free=sync_free)
+                              sync_free=sync_free, fixed_capacity=int(fixed_capacity))
     info: dict = {}
     if grad_sink is not None:
         # dict with fp32 contiguous buffers shaped like the six parameters (keys: means, quats, scales, opacities,

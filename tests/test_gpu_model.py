@@ -178,3 +178,37 @@ def test_fused_l1_and_u8_conversion_match_torch():
         torch.testing.assert_close(pred.grad, ref_p.grad, rtol=1e-6, atol=1e-9)
     assert torch.equal(u8_to_float(gt8), gtf)
     assert torch.equal(u8_to_float(gt8, 255.0, 10 / 255.0), gtf.clamp(min=10 / 255.0))
+
+
+@needs_cuda
+def test_cuda_graph_step_matches_eager_step():
+    """One captured training view (zero grads -> get_outputs -> get_loss_dict -> backward) replayed for two different
+    cameras must reproduce the eager loss and gradients of those cameras."""
+    from dn_splatter_b200.graph_step import GraphedTrainStep
+    from dn_splatter_b200.losses import DepthLossType
+    from dn_splatter_b200.synthetic import ring_cameras
+
+    params, _ = scene_and_camera(4000, 160, 128)
+    cams = [_camera(c) for c in ring_cameras(6, 160, 128)]
+    for c in cams:
+        c.camera_to_worlds = c.camera_to_worlds.cpu()
+    batch = {k: v.cuda() for k, v in _batch(128, 160).items()}
+    kw = dict(use_depth_loss=True, depth_lambda=0.2, depth_loss_type=DepthLossType.EdgeAwareLogL1, ssim_lambda=0.0,
+              sync_free=True)
+    m = _model(params, **kw)
+    bucket = m.enable_flat_grads()
+    eager = {}
+    for i in (0, 1, 2, 4):  # also seeds the intersection-capacity statistics the capture needs
+        bucket.zero_()
+        ld = m.get_loss_dict(m.get_outputs(cams[i]), dict(batch))
+        (ld["main_loss"] + ld["scale_reg"]).backward()
+        eager[i] = (float(ld["main_loss"] + ld["scale_reg"]), bucket.flat.clone())
+    step = GraphedTrainStep(m, bucket, cams[0], batch, n_slots=2)
+    for i, slot in ((4, 0), (1, 1), (2, 0)):
+        for k, v in batch.items():
+            step.batches[slot][k].copy_(v)
+        loss = step(cams[i], slot)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - eager[i][0]) <= 1e-5 * max(1.0, abs(eager[i][0])), (i, float(loss), eager[i][0])
+        rel = float((bucket.flat - eager[i][1]).norm() / (eager[i][1].norm() + 1e-30))
+        assert rel < 1e-4, (i, rel)

@@ -262,6 +262,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU: there is no CPU fallback"
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    torch.cuda.set_stream(torch.cuda.Stream(device=device))  # never the legacy default stream (CUDA-graph friendly)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     normals = not args.no_normals

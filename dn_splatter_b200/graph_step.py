@@ -48,6 +48,15 @@ class GraphedTrainStep:
             for k, v in example_batch.items():
                 b[k].copy_(v)
         self.load_camera(example_camera)
+        # Autograd graphs of earlier eager steps keep the parameters' AccumulateGrad nodes alive, and those remember the
+        # stream they were created on (usually the legacy default stream, which may not take part in a capture):
+        # drop the model's cached outputs so the nodes are rebuilt on the warm-up / capture streams.
+        import gc
+
+        for name in ("raster_out", "xys", "xys_flat", "radii", "depths", "conics", "num_tiles_hit"):
+            if name in model.__dict__:
+                model.__dict__[name] = None
+        gc.collect()
         # warm-up on a side stream (allocator pools, cub temp sizes), then one graph per batch slot
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())

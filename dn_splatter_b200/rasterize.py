@@ -233,6 +233,7 @@ class _DnRasterize(torch.autograd.Function):
         n_tiles = tiles_x * tiles_y
         rec_f = L.REC_FLOATS_N if s.render_normals else L.REC_FLOATS
         st = _stream()
+        ctx.fwd_stream = torch.cuda.current_stream()
 
         radii = torch.empty(n, **i32)
         means2d = torch.empty(n, 2, **f32)
@@ -318,6 +319,13 @@ class _DnRasterize(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, v_rgb, v_depth, v_normal, v_alpha, *_unused):
+        # run on the forward's stream explicitly (the autograd worker thread's current stream is not guaranteed to be
+        # it for foreign launches, and under CUDA-graph capture anything on another stream invalidates the capture)
+        with torch.cuda.stream(ctx.fwd_stream):
+            return _DnRasterize._backward(ctx, v_rgb, v_depth, v_normal, v_alpha)
+
+    @staticmethod
+    def _backward(ctx, v_rgb, v_depth, v_normal, v_alpha):
         lib = L.load()
         s: RasterSettings = ctx.settings
         means, quats, scales, opac, sh_dc, sh_rest, viewmat, K, c2w = ctx.saved_tensors

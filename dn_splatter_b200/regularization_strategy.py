@@ -59,12 +59,18 @@ class _FusedDNLoss(torch.autograd.Function):
             setattr(a, k, None if t is None else t.data_ptr())
         L.check(lib.dnr_loss_fwd(C.byref(a), _stream()), "dnr_loss_fwd")
         ctx.keep = (pd, pn, gd, gn, gi, partials)
+        ctx.fwd_stream = torch.cuda.current_stream()
         ctx.cfg = (W, H, int(depth_type), int(bool(use_normal)), float(depth_lambda), float(depth_tolerance))
         ctx.shapes = (None if pred_depth is None else pred_depth.shape, None if pred_normal is None else pred_normal.shape)
         return partials[11].clone()
 
     @staticmethod
     def backward(ctx, v):
+        with torch.cuda.stream(ctx.fwd_stream):
+            return _FusedDNLoss._backward(ctx, v)
+
+    @staticmethod
+    def _backward(ctx, v):
         lib = L.load()
         pd, pn, gd, gn, gi, partials = ctx.keep
         W, H, depth_type, use_normal, lam, tol = ctx.cfg
@@ -95,10 +101,16 @@ class _ScaleLoss(torch.autograd.Function):
         out = torch.empty(1, dtype=torch.float32, device=s.device)
         L.check(lib.dnr_scale_loss_fwd(s.data_ptr(), s.shape[0], out.data_ptr(), _stream()), "dnr_scale_loss_fwd")
         ctx.s = s
+        ctx.fwd_stream = torch.cuda.current_stream()
         return out[0].clone()
 
     @staticmethod
     def backward(ctx, v):
+        with torch.cuda.stream(ctx.fwd_stream):
+            return _ScaleLoss._backward(ctx, v)
+
+    @staticmethod
+    def _backward(ctx, v):
         lib = L.load()
         s = ctx.s
         v = v.detach().float().contiguous()
@@ -126,10 +138,16 @@ class FusedL1(torch.autograd.Function):
                 "dnr_l1_fwd")
         ctx.keep = (p, g)
         ctx.shape = pred.shape
+        ctx.fwd_stream = torch.cuda.current_stream()
         return out[0].clone()
 
     @staticmethod
     def backward(ctx, v):
+        with torch.cuda.stream(ctx.fwd_stream):
+            return FusedL1._backward(ctx, v)
+
+    @staticmethod
+    def _backward(ctx, v):
         lib = L.load()
         p, g = ctx.keep
         v = v.detach().float().contiguous()

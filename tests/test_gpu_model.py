@@ -203,6 +203,7 @@ def test_cuda_graph_step_matches_eager_step():
         ld = m.get_loss_dict(m.get_outputs(cams[i]), dict(batch))
         (ld["main_loss"] + ld["scale_reg"]).backward()
         eager[i] = (float(ld["main_loss"] + ld["scale_reg"]), bucket.flat.clone())
+    del ld  # a live autograd graph would pin AccumulateGrad nodes created on the default stream (see graph_step.py)
     step = GraphedTrainStep(m, bucket, cams[0], batch, n_slots=2)
     for i, slot in ((4, 0), (1, 1), (2, 0)):
         for k, v in batch.items():

@@ -9,6 +9,9 @@ What makes the step capturable (see rasterize.py / dn_model.py):
     pinned H2D copy before each replay (resolution must not change between replays);
   * the supervision maps live in static device buffers that the caller fills (H2D or D2D) before each replay;
   * gradients go to the flat bucket (static addresses); the loss is a static 0-dim tensor.
+Run the training loop on a non-default stream (`torch.cuda.set_stream(torch.cuda.Stream())`): the legacy default
+stream cannot take part in a capture and autograd pins each parameter's gradient accumulator to the stream it was
+first used on.
 """
 from __future__ import annotations
 

@@ -184,6 +184,13 @@ def test_fused_l1_and_u8_conversion_match_torch():
 def test_cuda_graph_step_matches_eager_step():
     """One captured training view (zero grads -> get_outputs -> get_loss_dict -> backward) replayed for two different
     cameras must reproduce the eager loss and gradients of those cameras."""
+    # the whole loop lives on a non-default stream: the legacy stream cannot take part in a capture, and autograd
+    # remembers the stream each parameter's gradient accumulator was created on (see graph_step.py)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        _graph_step_body()
+
+
+def _graph_step_body():
     from dn_splatter_b200.graph_step import GraphedTrainStep
     from dn_splatter_b200.losses import DepthLossType
     from dn_splatter_b200.synthetic import ring_cameras

@@ -264,7 +264,9 @@ def main():
     device = torch.device("cuda", local_rank)
     torch.cuda.set_stream(torch.cuda.Stream(device=device))  # never the legacy default stream (CUDA-graph friendly)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     normals = not args.no_normals
     import dn_splatter_b200.rasterize as R
 
@@ -368,7 +370,8 @@ def main():
     for s in range(max(3, args.warmup)):
         resident_step(s)
     launches_per_step = None
-    if not args.no_graph:
+    # multi-rank runs launch eagerly: graph capture next to NCCL's watchdog thread is not validated yet
+    if not args.no_graph and world == 1:
         from dn_splatter_b200 import _lib as _L0
         from dn_splatter_b200.graph_step import GraphedTrainStep
 

@@ -456,8 +456,14 @@ def main():
         }
         dom = max((k for k in stages if k in alg), key=lambda k: stages[k])
         ach = alg[dom] / (stages[dom] / 1e3) / 1e9
+        traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            t = _jl(open(tpath))
+            key = f"{dom}:{args.n_gauss}:{args.width}x{args.height}:{'n' if normals else 'c'}"
+            traffic = t.get(key, {}).get("dram_bytes_per_launch")
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
                 "n_isects": I, "n_isects_composited": i_eff, "ms_per_launch": stages[dom]}
 
     cpu = None

@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--no-normals", action="store_true", help="BASELINE config C2 literal: RGB+depth only")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--cpu-crop", default="256x144")
+    ap.add_argument("--cpu-crop", default="512x288")
     ap.add_argument("--sync", action="store_true", help="read the intersection count back every view (host sync)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph captured step")
     return ap.parse_args()

@@ -201,20 +201,24 @@ __global__ void __launch_bounds__(256) count_kernel(const DnrArgs a, const int32
   counts[i] = (i < a.n_gauss) ? cnt : 0;
 }
 
-// One warp per 32 depth-sorted Gaussians; for each Gaussian the lanes take its tile rows, compute the row spans, scan
-// their lengths and write the spans (row-major, ascending x: the order gsplat emits).  Entries past the capacity are
-// dropped (the caller sees n_isects_dev > capacity and retries).
+// One warp per EMIT_GPW depth-sorted Gaussians (their parameters are loaded one per lane, in parallel); for each Gaussian
+// the lanes take its tile rows, compute the row spans, scan their lengths and write the spans (row-major, ascending x:
+// the order gsplat emits).  Few Gaussians per warp = more warps in flight: the kernel is latency-bound.  Entries past
+// the capacity are dropped (the caller sees n_isects_dev > capacity and retries).
+constexpr int EMIT_GPW = 8;
+
 template <typename KeyT>
 __global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_t* __restrict__ order,
                                                   const int64_t* __restrict__ isect_start, KeyT* __restrict__ keys,
                                                   int32_t* __restrict__ gids, int tiles_x, int tiles_y) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int base = warp * 32;
+  const int base = warp * EMIT_GPW;
   if (base >= a.n_gauss) return;
-  const HitGauss mine = load_hit_gauss(a, order, base + lane, tiles_x, tiles_y);
-  const int64_t my_start = (base + lane < a.n_gauss) ? isect_start[base + lane] : 0;
-  const int64_t my_end = (base + lane < a.n_gauss) ? isect_start[base + lane + 1] : 0;
+  const bool loader = lane < EMIT_GPW && base + lane < a.n_gauss;
+  const HitGauss mine = load_hit_gauss(a, order, loader ? base + lane : a.n_gauss, tiles_x, tiles_y);
+  const int64_t my_start = loader ? isect_start[base + lane] : 0;
+  const int64_t my_end = loader ? isect_start[base + lane + 1] : 0;
   const int64_t cap = a.n_isects;
   const bool exact = (a.flags & DNR_FLAG_EXACT_LISTS) != 0;
   unsigned todo = __ballot_sync(0xffffffffu, my_end > my_start);
@@ -287,7 +291,7 @@ int bin_sort_impl(const DnrArgs* a, cudaStream_t s, int n_tiles, int tile_bits) 
   const int64_t cap = a->n_isects;
   SortWs<KeyT> w = carve_sort<KeyT>(a->ws_sort, cap, tile_bits);
   if (cap > 0) {
-    const int64_t threads = (((int64_t)a->n_gauss + 31) / 32) * 32;  // one warp per 32 Gaussians
+    const int64_t threads = (((int64_t)a->n_gauss + EMIT_GPW - 1) / EMIT_GPW) * 32;  // one warp per EMIT_GPW Gaussians
     emit_kernel<KeyT><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(*a, sw.order, sw.isect_start, w.keys_in, w.gids_in,
                                                                           tiles_x, tiles_y);
     DNR_CHECK_LAUNCH();

@@ -39,33 +39,6 @@ __device__ __forceinline__ void dnr_tile_box(float mx, float my, int radius, int
   y1 = min(max((int)ceilf(tcy + r), 0), tiles_y);
 }
 
-// Conservative precise-hit test used when emitting intersections: can the Gaussian (centre m, conic A,B,C)
-// reach sigma <= lim anywhere on the pixel-centre rectangle [x0,x1]x[y0,y1]?  sigma is a convex quadratic, so
-// its minimum over the rectangle is 0 (centre inside) or lies on the edge(s) facing the centre.  boc = B/C and
-// boa = B/A are per-Gaussian constants (hoisted divisions).  Each candidate is lowered by a bound on its own
-// rounding error (terms can cancel for needle-like splats), so the test only errs on the keeping side.
-__device__ __forceinline__ bool dnr_rect_hit(float mx, float my, float A, float B, float C, float boc, float boa, float lim,
-                                             float x0, float x1, float y0, float y1) {
-  const bool in_x = (mx >= x0) && (mx <= x1), in_y = (my >= y0) && (my <= y1);
-  if (in_x && in_y) return true;
-  float qmin = 3.0e38f;
-  if (!in_x) {
-    const float dx = mx - (mx < x0 ? x0 : x1);
-    const float ys = fminf(fmaxf(my + boc * dx, y0), y1);
-    const float dy = my - ys;
-    const float t0 = A * dx * dx, t1 = C * dy * dy, t2 = B * dx * dy;
-    qmin = 0.5f * (t0 + t1) + t2 - 4e-6f * (fabsf(t0) + fabsf(t1) + fabsf(t2));
-  }
-  if (!in_y) {
-    const float dy = my - (my < y0 ? y0 : y1);
-    const float xs = fminf(fmaxf(mx + boa * dy, x0), x1);
-    const float dx = mx - xs;
-    const float t0 = A * dx * dx, t1 = C * dy * dy, t2 = B * dx * dy;
-    qmin = fminf(qmin, 0.5f * (t0 + t1) + t2 - 4e-6f * (fabsf(t0) + fabsf(t1) + fabsf(t2)));
-  }
-  return qmin <= lim;
-}
-
 // log2-domain exponent of a splat at offset (dx,dy): records hold a' = -0.5*log2(e)*A, b' = -log2(e)*B,
 // c' = -0.5*log2(e)*C, so alpha = opac * 2^power.  Fixed rounding order, shared by the forward and backward
 // kernels so that both take the same skip/stop branches for every (pixel, Gaussian) pair.

@@ -135,6 +135,14 @@ class DNSplatterModelConfig:
     reset_alpha_every: int = 30
     resolution_schedule: int = 3000
     cull_alpha_thresh: float = 0.1
+    cull_scale_thresh: float = 0.5
+    cull_screen_size: float = 0.15
+    split_screen_size: float = 0.05
+    stop_screen_size_at: int = 4000
+    densify_grad_thresh: float = 0.0008
+    densify_size_thresh: float = 0.01
+    n_split_samples: int = 2
+    continue_cull_post_densification: bool = True
     # ---- dn_splatter_b200 options (not in the reference) ----
     exact_isect_lists: bool = False
     """Emit gsplat's full bbox tile lists instead of the precise-hit lists (parity debugging; images are identical)."""
@@ -517,3 +525,38 @@ class DNSplatterModel(torch.nn.Module):
 
     def step_cb(self, step: int):
         self.step = step
+
+    # ------------------------------------------------------------------ densification (densify.py)
+    def _densify_cfg(self):
+        from .densify import DensifyConfig
+
+        c = self.config
+        return DensifyConfig(
+            warmup_length=c.warmup_length, refine_every=c.refine_every, reset_alpha_every=c.reset_alpha_every,
+            stop_split_at=c.stop_split_at, stop_screen_size_at=c.stop_screen_size_at,
+            densify_grad_thresh=c.densify_grad_thresh, densify_size_thresh=c.densify_size_thresh,
+            n_split_samples=c.n_split_samples, split_screen_size=c.split_screen_size, cull_alpha_thresh=c.cull_alpha_thresh,
+            cull_scale_thresh=c.cull_scale_thresh, cull_screen_size=c.cull_screen_size,
+            continue_cull_post_densification=c.continue_cull_post_densification)
+
+    def after_train(self, step: int):
+        """SplatfactoModel.after_train [EXT]: accumulate the view's absgrad / radii statistics."""
+        from .densify import DensifyState
+
+        assert step == self.step
+        if self.__dict__.get("_densify_state") is None:
+            self.__dict__["_densify_state"] = DensifyState()
+        absgrad = getattr(self.xys_flat, "absgrad", None)
+        if absgrad is not None:
+            self._densify_state.after_train(absgrad, self.radii, self.last_size)
+
+    def refinement_after(self, optimizers, step: int, generator=None):
+        """Reference dn_model.py:271-386.  `optimizers`: {param name: torch optimizer} (densify.build_optimizers) or a
+        nerfstudio `Optimizers` object exposing `.optimizers`."""
+        from .densify import DensifyState, refinement_after
+
+        assert step == self.step
+        opts = getattr(optimizers, "optimizers", optimizers)
+        state = self.__dict__.get("_densify_state") or DensifyState()
+        self.__dict__["_densify_state"] = state
+        return refinement_after(self, opts, step, state, self._densify_cfg(), self.num_train_data, generator)

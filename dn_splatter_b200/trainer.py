@@ -1,0 +1,51 @@
+"""A minimal training loop standing in for nerfstudio's Trainer [EXT] around the hot path: per-group Adam with the
+reference's learning rates (dn_config.py:29-68), the callback order of SURVEY §3.1 (step_cb -> forward -> losses ->
+backward -> [all-reduce] -> optimizer step -> after_train -> refinement every `refine_every`), per-camera sharding
+over ranks.  Eager launches (the Gaussian count changes at refinements; capture a GraphedTrainStep between them if
+wanted)."""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional
+
+import torch
+
+from .densify import build_optimizers, exponential_lr
+from .dn_config import MAX_NUM_ITERATIONS, optimizer_groups
+
+
+class Trainer:
+    def __init__(self, model, next_train: Callable[[int], tuple], max_steps: int = MAX_NUM_ITERATIONS,
+                 world_size: int = 1, seed: int = 0):
+        self.model, self.next_train, self.max_steps = model, next_train, max_steps
+        self.groups = optimizer_groups(max_steps)
+        self.optimizers: Dict[str, torch.optim.Optimizer] = build_optimizers(model, self.groups)
+        self.bucket = model.enable_flat_grads()
+        self.world_size = world_size
+        self.generator = torch.Generator().manual_seed(seed)  # identical on every rank: identical split samples
+        self.step = 0
+
+    def train_iteration(self) -> Dict[str, float]:
+        m, step = self.model, self.step
+        m.train()
+        m.step_cb(step)
+        camera, batch = self.next_train(step)
+        self.bucket = m._bucket or m.enable_flat_grads()
+        self.bucket.zero_()
+        outputs = m.get_outputs(camera)
+        loss_dict = m.get_loss_dict(outputs, batch)
+        loss = loss_dict["main_loss"] + loss_dict["scale_reg"]
+        loss.backward()
+        if self.world_size > 1:
+            self.bucket.all_reduce()
+        for name, opt in self.optimizers.items():
+            g = self.groups[name]
+            if g.get("lr_final"):
+                for pg in opt.param_groups:
+                    pg["lr"] = exponential_lr(g["lr"], g["lr_final"], step, g["max_steps"])
+            opt.step()
+        m.after_train(step)
+        info: Optional[Dict[str, int]] = None
+        if step > 0 and step % m.config.refine_every == 0:
+            info = m.refinement_after(self.optimizers, step, generator=self.generator)
+        self.step += 1
+        return {"loss": loss.detach(), "refine": info}

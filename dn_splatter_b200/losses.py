@@ -123,12 +123,12 @@ class TVLoss(nn.Module):
 
 
 class PearsonDepthLoss(nn.Module):
-    """reference losses.py:428-452: 1 - Pearson correlation of flattened depths."""
+    """reference losses.py:428-452: 1 - mean(z(pred) * z(gt)) with z(x) = (x - mean) / (unbiased std + 1e-6)."""
 
     def forward(self, pred, gt):
-        p, g = pred.reshape(-1), gt.reshape(-1)
-        p, g = p - p.mean(), g - g.mean()
-        co = (p * g).sum() / (p.norm() * g.norm() + 1e-12)
+        zp = (pred - pred.mean()) / (pred.std() + 1e-6)
+        zg = (gt - gt.mean()) / (gt.std() + 1e-6)
+        co = (zp * zg).mean()
         assert not torch.any(torch.isnan(co))
         return 1 - co
 

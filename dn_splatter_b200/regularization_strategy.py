@@ -287,6 +287,10 @@ class AGSMeshRegularization(RegularizationStrategy):
         n = self.get_normal_loss(step, surf_normal, gt_normal, pred_normal)
         return d + n + self.get_scale_loss(scales=kwargs["scales"])
 
+    def get_scale_loss(self, scales):
+        """Plain torch (this strategy is the torch-executed one; reference :322-327)."""
+        return torch.min(torch.exp(scales), dim=1, keepdim=True)[0].mean()
+
     def get_depth_loss(self, step, pred_depth, gt_depth, confidence_map, **kwargs):
         if step >= 7000:  # hard-coded in the reference (:275), not depth_mask_steps
             gt_depth = torch.where(confidence_map > 0, gt_depth, torch.zeros_like(gt_depth))

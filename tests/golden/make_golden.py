@@ -106,6 +106,50 @@ def main():
         inp = dict(pred_depth=pred_depth, gt_depth=gt_depth, pred_normal=pred_normal, gt_normal=gt_normal,
                    gt_img=gt_img, scales=scales, intr=torch.tensor([fx, fy, cx, cy], dtype=torch.float64))
         cases[tag] = (inp, out)
+    # ---- the nn.Module surface of losses.py and the AGS-Mesh strategy (torch paths of this repo) -------------------
+    from dn_splatter.losses import EdgeAwareTV, HuberL1, PearsonDepthLoss
+    from dn_splatter.regularization_strategy import AGSMeshRegularization, find_edges, mean_angular_error
+
+    H, W = 20, 28
+    pd = 0.5 + 4 * torch.rand(H, W, 1, generator=g)
+    gd = pd + 0.3 * torch.randn(H, W, 1, generator=g)
+    gd[torch.rand(H, W, 1, generator=g) < 0.15] = 0.0
+    img = torch.rand(H, W, 3, generator=g).clamp(min=10 / 255.0)
+    mask = gd > 0.1
+    mod_in = dict(pd=pd, gd=gd, img=img)
+    mod_out = {
+        "edge_aware_logl1_pp": EdgeAwareLogL1(implementation="per-pixel")(pd, gd, img, mask),
+        "logl1_pp": LogL1(implementation="per-pixel")(pd, gd),
+        "l1_pp": L1(implementation="per-pixel")(pd, gd),
+        "huber": HuberL1()(pd, gd),
+        "edge_aware_tv": EdgeAwareTV()(pd[None], img[None]),
+        "pearson": PearsonDepthLoss()(pd, gd + 0.01),
+        "mse": DepthLoss(DepthLossType.MSE)(pd, gd),
+    }
+    # AGS-Mesh: [C,H,W] normals in [-1,1]
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    gn = torch.stack([0.3 + 0.1 * torch.sin(xx / 3), 0.4 + 0.1 * torch.cos(yy / 4), 0.8 + 0 * xx])
+    gn[:, :, W // 2:] = gn[:, :, W // 2:].flip(0)  # one crease: find_edges should fire there and only there
+    gn = torch.nn.functional.normalize(gn, dim=0)
+    sn = torch.nn.functional.normalize(gn + 0.05 * torch.randn(3, H, W, generator=g), dim=0)
+    pn = torch.nn.functional.normalize(torch.randn(3, H, W, generator=g), dim=0)
+    conf = (torch.rand(H, W, 1, generator=g) > 0.3).float()
+    scales = torch.randn(40, 3, generator=g) - 3
+    mod_in.update(sn=sn, gn=gn, pn=pn, conf=conf, scales=scales)
+    mod_out["find_edges_3"] = find_edges(gn).float()
+    mod_out["find_edges_1"] = find_edges(pd.permute(2, 0, 1)).float()
+    mod_out["mean_angular_error"] = mean_angular_error(sn, gn)
+    ags = AGSMeshRegularization()
+    for step in (100, 8000, 16000):
+        mod_out[f"ags_normal_{step}"] = torch.as_tensor(ags.get_normal_loss(step, sn, gn, pn)).float()
+    mod_out["ags_depth_100"] = ags.get_depth_loss(step=100, pred_depth=pd, gt_depth=gd, confidence_map=conf, gt_img=img)
+    mod_out["ags_total_100"] = ags(step=100, pred_depth=pd, gt_depth=gd, surf_normal=sn, gt_normal=gn, pred_normal=pn,
+                                   confidence_map=conf, scales=scales, gt_img=img)
+    arrs = {f"in_{k}": v.detach().numpy() for k, v in mod_in.items()}
+    arrs.update({f"out_{k}": v.detach().numpy() for k, v in mod_out.items()})
+    np.savez_compressed(os.path.join(OUT, "dn_reference_modules.npz"), **arrs)
+    print("modules", {k: tuple(v.shape) for k, v in arrs.items() if k.startswith("out_")})
+
     for tag, (inp, out) in cases.items():
         arrs = {f"in_{k}": v.detach().numpy() for k, v in inp.items()}
         arrs.update({f"out_{k}": v.detach().numpy() for k, v in out.items()})

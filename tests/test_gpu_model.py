@@ -117,7 +117,7 @@ def test_normal_from_depth_image_matches_reference_goldens(golden_dir):
 
     from dn_splatter_b200.utils.normal_utils import normal_from_depth_image
 
-    for f in sorted(glob.glob(os.path.join(golden_dir, "dn_reference_*.npz"))):
+    for f in sorted(glob.glob(os.path.join(golden_dir, "dn_reference_[ab].npz"))):
         z = np.load(f)
         d = torch.from_numpy(z["in_pred_depth"]).cuda()
         fx, fy, cx, cy = [float(v) for v in z["in_intr"]]
@@ -136,7 +136,7 @@ def test_dn_regularization_matches_reference_goldens(golden_dir):
     from dn_splatter_b200.losses import DepthLoss, DepthLossType
     from dn_splatter_b200.regularization_strategy import DNRegularization
 
-    for f in sorted(glob.glob(os.path.join(golden_dir, "dn_reference_*.npz"))):
+    for f in sorted(glob.glob(os.path.join(golden_dir, "dn_reference_[ab].npz"))):
         z = {k: torch.from_numpy(v).cuda() for k, v in np.load(f).items()}
         for key, lam, t in (("dn_reg_lambda0.2", 0.2, None), ("dn_reg_lambda0.5", 0.5, None),
                             ("dn_reg_LogL1", 0.2, DepthLossType.LogL1), ("dn_reg_L1", 0.2, DepthLossType.L1),

@@ -370,17 +370,22 @@ def main():
             model.get_outputs(cams[v])
     for s in range(max(3, args.warmup)):
         resident_step(s)
-    launches_per_step = None
+    launches_per_step, graph_error = None, None
     # multi-rank runs launch eagerly: graph capture next to NCCL's watchdog thread is not validated yet
     if not args.no_graph and world == 1:
         from dn_splatter_b200 import _lib as _L0
         from dn_splatter_b200.graph_step import GraphedTrainStep
 
         l0 = dict(_L0.LAUNCHES)
-        graphed = GraphedTrainStep(model, bucket, cams[my_views[0]], dev_sets[0], n_slots=3, warmup=2)
-        n_eager = 2 + 3  # warm-up calls + one capture per slot
-        launches_per_step = {k: (_L0.LAUNCHES[k] - l0[k]) // n_eager for k in l0}
-        use_graph_buffers()
+        try:
+            graphed = GraphedTrainStep(model, bucket, cams[my_views[0]], dev_sets[0], n_slots=3, warmup=2)
+        except Exception as exc:  # noqa: BLE001 — keep measuring with eager launches rather than losing the run
+            graphed, graph_error = None, f"{type(exc).__name__}: {exc}"[:300]
+            torch.cuda.synchronize()
+        if graphed is not None:
+            n_eager = 2 + 3  # warm-up calls + one capture per slot
+            launches_per_step = {k: (_L0.LAUNCHES[k] - l0[k]) // n_eager for k in l0}
+            use_graph_buffers()
         for s in range(3):
             resident_step(s)
     sampler = ClockSampler(local_rank)
@@ -414,7 +419,8 @@ def main():
 
     # per-stage device times (CUDA events on the launching stream) for the roofline of the dominant kernel
     stages, roof = {}, None
-    graph_info = None if graphed is None else {"capacity": graphed.capacity, "slots": len(graphed.graphs)}
+    graph_info = ({"capacity": graphed.capacity, "slots": len(graphed.graphs)} if graphed is not None
+                  else ({"error": graph_error, "fallback": "eager launches"} if graph_error else None))
     graphed = None  # the instrumented pass below runs eagerly
     if rank == 0:
         R.STAGE_EVENTS = []

@@ -370,6 +370,12 @@ __global__ void __launch_bounds__(PB_THREADS, 8) project_bwd_kernel(const DnrArg
   const int radius = in_range ? a.radii[i] : 0;
   const bool visible = radius > 0;
   s_vis[threadIdx.x] = visible ? 1 : 0;
+  // means2d.grad / .absgrad (what densification reads) are plain outputs, not accumulators: invisible rows are zero in
+  // every mode (the caller hands in uninitialised buffers)
+  if (in_range && !visible) {
+    if (a.v_means2d) { a.v_means2d[i * 2] = 0.f; a.v_means2d[i * 2 + 1] = 0.f; }
+    if (a.v_means2d_abs) { a.v_means2d_abs[i * 2] = 0.f; a.v_means2d_abs[i * 2 + 1] = 0.f; }
+  }
   float* srow = s_rest + threadIdx.x * PB_REST_MAX;
   // visible rows are fully written by the SH section below; invisible rows are only read by the dense-overwrite path
   if (!visible && !acc) {
@@ -382,8 +388,6 @@ __global__ void __launch_bounds__(PB_THREADS, 8) project_bwd_kernel(const DnrArg
     for (int k = 0; k < 3; ++k) { a.v_means[i * 3 + k] = 0.f; a.v_scales[i * 3 + k] = 0.f; a.v_sh_dc[i * 3 + k] = 0.f; }
     for (int k = 0; k < 4; ++k) a.v_quats[i * 4 + k] = 0.f;
     a.v_opacities[i] = 0.f;
-    if (a.v_means2d) { a.v_means2d[i * 2] = 0.f; a.v_means2d[i * 2 + 1] = 0.f; }
-    if (a.v_means2d_abs) { a.v_means2d_abs[i * 2] = 0.f; a.v_means2d_abs[i * 2 + 1] = 0.f; }
   }
   if (visible) {
   Cam cam;

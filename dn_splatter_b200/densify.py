@@ -63,11 +63,11 @@ class DensifyState:
             self.xys_grad_norm = torch.zeros(n, device=radii.device, dtype=torch.float32)
             self.vis_counts = torch.ones(n, device=radii.device, dtype=torch.float32)
             self.max_2Dsize = torch.zeros(n, device=radii.device, dtype=torch.float32)
-        visf = vis.to(torch.float32)
-        self.vis_counts += visf
-        self.xys_grad_norm += absgrad.norm(dim=-1) * visf
+        zero = torch.zeros((), device=radii.device, dtype=torch.float32)
+        self.vis_counts += vis.to(torch.float32)
+        self.xys_grad_norm += torch.where(vis, absgrad.norm(dim=-1), zero)  # where(): never touches invisible rows
         rel = radii.to(torch.float32) / float(max(last_size[0], last_size[1]))
-        self.max_2Dsize = torch.maximum(self.max_2Dsize, rel * visf)
+        self.max_2Dsize = torch.maximum(self.max_2Dsize, torch.where(vis, rel, zero))
 
 
 def _quat_to_rotmat(q: Tensor) -> Tensor:

@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            defs = [f"-D{k}={os.environ[k]}" for k in ("DNR_BWD_PPT",) if k in os.environ]  # tuning knobs
+            defs = [f"-D{k}={os.environ[k]}" for k in ("DNR_BWD_PPT", "DNR_EMIT_ROWWISE") if k in os.environ]  # tuning knobs
             cmd = [nvcc, *ARCH, *COMMON, *extra, *defs, "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")

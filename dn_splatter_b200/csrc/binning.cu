@@ -206,6 +206,9 @@ __global__ void __launch_bounds__(256) count_kernel(const DnrArgs a, const int32
 // the order gsplat emits).  Few Gaussians per warp = more warps in flight: the kernel is latency-bound.  Entries past
 // the capacity are dropped (the caller sees n_isects_dev > capacity and retries).
 constexpr int EMIT_GPW = 8;
+#ifndef DNR_EMIT_ROWWISE
+#define DNR_EMIT_ROWWISE 0
+#endif
 
 template <typename KeyT>
 __global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_t* __restrict__ order,
@@ -238,6 +241,25 @@ __global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_
         const int v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
       }
+#if DNR_EMIT_ROWWISE
+      // round-2 candidate (not yet validated on a GPU, off by default): walk the rows uniformly and let the lanes write
+      // one row's span side by side -> contiguous 2 B / 4 B stores (1-2 sectors per row instead of one per lane).
+      // profiles/launches_r1d_step.txt: emit_kernel is 189 us for 69 MB, i.e. bound by partial-sector store transactions.
+      const int rows_here = min(32, h.ny - r0);
+      for (int rr = 0; rr < rows_here; ++rr) {
+        const int len_r = __shfl_sync(0xffffffffu, len, rr);
+        if (len_r == 0) continue;
+        const int lo_r = __shfl_sync(0xffffffffu, lo, rr);
+        const int64_t dst_r = dst0 + __shfl_sync(0xffffffffu, incl - len, rr);
+        const int key_r = (h.y0 + r0 + rr) * tiles_x + lo_r;
+        for (int k = lane; k < len_r; k += 32) {
+          if (dst_r + k < cap) {
+            keys[dst_r + k] = (KeyT)(key_r + k);
+            gids[dst_r + k] = h.g;
+          }
+        }
+      }
+#else
       const int64_t dst = dst0 + (incl - len);
       const int row_key = (h.y0 + r) * tiles_x;
       for (int k = 0; k < len; ++k) {
@@ -246,6 +268,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_
           gids[dst + k] = h.g;
         }
       }
+#endif
       dst0 += __shfl_sync(0xffffffffu, incl, 31);
     }
   }

@@ -373,6 +373,12 @@ class DNSplatterModel(torch.nn.Module):
             raise NotImplementedError("crop boxes are viewer-only and outside the hot path")
         if cfg.rasterize_mode not in ("antialiased", "classic"):
             raise ValueError("Unknown rasterize_mode: %s", cfg.rasterize_mode)
+        if cfg.rasterize_mode == "antialiased" and cfg.predict_normals and not self.__dict__.get("_warned_aa"):
+            import warnings
+
+            warnings.warn("rasterize_mode='antialiased' with predict_normals: the normal image is composited with the "
+                          "compensated opacity (the reference's legacy pass uses the un-compensated one); see DESIGN.md §2")
+            self.__dict__["_warned_aa"] = True
         if cfg.sh_degree <= 0:
             raise NotImplementedError("sh_degree == 0 (sigmoid colours) is broken upstream (SURVEY A1.4); not mirrored")
         scale_fac = self._get_downscale_factor()

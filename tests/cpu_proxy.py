@@ -53,7 +53,10 @@ def cpu_proxy():
     import dn_splatter_b200.dn_model as M
     import dn_splatter_b200.regularization_strategy as RS
 
-    saved = (M.dn_rasterize, M.FusedL1, M.u8_to_float, RS._FusedDNLoss, RS._ScaleLoss)
+    saved = (M.dn_rasterize, M.FusedL1, M.u8_to_float, RS._FusedDNLoss, RS._ScaleLoss, M.normal_from_depth_image)
+
+    def nfd(depths, fx, fy, cx, cy, img_size, c2w, device, smooth=False):
+        return dn_ref.normal_from_depth_image(depths, fx, fy, cx, cy, int(img_size[0]), int(img_size[1]))
 
     class L1Proxy:
         @staticmethod
@@ -78,7 +81,8 @@ def cpu_proxy():
     M.dn_rasterize, M.FusedL1 = oracle_rasterize, L1Proxy
     M.u8_to_float = lambda img, divisor=255.0, clamp_min=0.0: (img.float() / divisor).clamp(min=clamp_min)
     RS._FusedDNLoss, RS._ScaleLoss = DNProxy, ScaleProxy
+    M.normal_from_depth_image = nfd
     try:
         yield
     finally:
-        M.dn_rasterize, M.FusedL1, M.u8_to_float, RS._FusedDNLoss, RS._ScaleLoss = saved
+        M.dn_rasterize, M.FusedL1, M.u8_to_float, RS._FusedDNLoss, RS._ScaleLoss, M.normal_from_depth_image = saved

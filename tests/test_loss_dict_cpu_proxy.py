@@ -1,0 +1,81 @@
+"""get_loss_dict control flow of the reference (dn_model.py:614-729) on the CPU through tests/cpu_proxy.py: mask handling
+(quirk B11), depth-source precedence, normal_supervision='depth', the ags-mesh strategy, and the documented errors."""
+import pytest
+import torch
+
+from oracle import dn_ref
+from tests.cpu_proxy import cpu_proxy
+
+
+def _setup(**kw):
+    from dn_splatter_b200.cameras import Cameras
+    from dn_splatter_b200.dn_model import DNSplatterModelConfig
+    from dn_splatter_b200.losses import DepthLossType
+    from dn_splatter_b200.synthetic import make_scene, ring_cameras
+
+    W, H = 40, 32
+    c = ring_cameras(3, W, H)[1]
+    cam = Cameras(c["c2w"][None], c["fx"], c["fy"], c["cx"], c["cy"], W, H)
+    base = dict(random_init=True, num_random=16, background_color="black", use_depth_loss=True, depth_lambda=0.2,
+                depth_loss_type=DepthLossType.EdgeAwareLogL1, ssim_lambda=0.0)
+    base.update(kw)
+    m = DNSplatterModelConfig(**base).setup(device="cpu")
+    m.load_gaussians(make_scene(60, seed=2))
+    m.step = 5000
+    m.train()
+    g = torch.Generator().manual_seed(0)
+    batch = {"image": (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8), "mono_depth": 2 + 5 * torch.rand(H, W, 1, generator=g),
+             "sensor_depth": 1 + torch.rand(H, W, 1, generator=g), "normal": torch.rand(H, W, 3, generator=g)}
+    return m, cam, batch, (H, W)
+
+
+def test_mono_depth_wins_over_sensor_depth_and_mask_is_applied_in_place():
+    with cpu_proxy():
+        m, cam, batch, (H, W) = _setup()
+        out = m.get_outputs(cam)
+        ld = m.get_loss_dict(out, dict(batch))
+        gt_img = (batch["image"].float() / 255.0)
+        want = (gt_img - out["rgb"]).abs().mean() + dn_ref.dn_regularization(
+            out["depth"], batch["mono_depth"], out["normal"], batch["normal"], m.scales, gt_img.clamp(min=10 / 255.0), depth_lambda=0.2)
+        torch.testing.assert_close(ld["main_loss"], want, rtol=1e-5, atol=1e-6)
+        assert float(ld["scale_reg"]) == 0.0
+        # with a mask: outputs["normal"] and batch["normal"] are multiplied in the dicts (quirk B11), rgb loss is masked too
+        mask = (torch.rand(H, W, 1, generator=torch.Generator().manual_seed(3)) > 0.3)
+        out2 = m.get_outputs(cam)
+        b2 = dict(batch, mask=mask)
+        n_before = out2["normal"].clone()
+        ld2 = m.get_loss_dict(out2, b2)
+        assert torch.equal(out2["normal"], n_before * mask) and torch.equal(b2["normal"], batch["normal"] * mask)
+        want2 = (gt_img * mask - out2["rgb"] * mask).abs().mean() + dn_ref.dn_regularization(
+            out2["depth"] * mask, batch["mono_depth"] * mask, n_before * mask, batch["normal"] * mask, m.scales,
+            gt_img.clamp(min=10 / 255.0), depth_lambda=0.2)
+        torch.testing.assert_close(ld2["main_loss"], want2, rtol=1e-5, atol=1e-6)
+
+
+def test_normal_supervision_from_depth_and_missing_depth_error():
+    with cpu_proxy():
+        m, cam, batch, (H, W) = _setup(normal_supervision="depth")
+        out = m.get_outputs(cam)
+        b = {k: v for k, v in batch.items() if k != "normal"}
+        ld = m.get_loss_dict(out, dict(b))
+        gt_n = dn_ref.surface_normal_output(out["depth"], float(cam.fx), float(cam.fy), float(cam.cx), float(cam.cy), W, H)
+        gt_img = (batch["image"].float() / 255.0)
+        want = (gt_img - out["rgb"]).abs().mean() + dn_ref.dn_regularization(
+            out["depth"], batch["mono_depth"], out["normal"], gt_n, m.scales, gt_img.clamp(min=10 / 255.0), depth_lambda=0.2)
+        torch.testing.assert_close(ld["main_loss"], want, rtol=1e-5, atol=1e-6)
+        # use_depth_loss without any depth in the batch: the reference dies on `None > tol`; we raise a TypeError too
+        with pytest.raises(TypeError):
+            m.get_loss_dict(m.get_outputs(cam), {"image": batch["image"], "normal": batch["normal"]})
+
+
+def test_ags_mesh_strategy_path_runs_and_needs_confidence():
+    with cpu_proxy():
+        m, cam, batch, (H, W) = _setup(regularization_strategy="ags-mesh")
+        out = m.get_outputs(cam)
+        yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+        smooth = torch.stack([0.8 + 0.05 * torch.sin(xx / 7), 0.7 + 0.05 * torch.cos(yy / 5), 0.9 + 0 * xx], dim=-1)
+        b = dict(batch, normal=smooth, confidence=torch.zeros(H, W, 1))  # (random normals are all "edges": NaN, as upstream)
+        ld = m.get_loss_dict(out, b)
+        assert torch.isfinite(ld["main_loss"])
+        with pytest.raises((NameError, UnboundLocalError, TypeError)):  # quirk B15: confidence is required
+            m.get_loss_dict(m.get_outputs(cam), dict(batch))

@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--cpu-crop", default="512x288")
     ap.add_argument("--sync", action="store_true", help="read the intersection count back every view (host sync)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph captured step")
+    ap.add_argument("--graph-multi", action="store_true", help="capture the step in a CUDA graph on multi-rank runs too "
+                                                                "(not validated in round 1; the all-reduce stays outside the graph)")
     return ap.parse_args()
 
 
@@ -372,7 +374,7 @@ def main():
         resident_step(s)
     launches_per_step, graph_error = None, None
     # multi-rank runs launch eagerly: graph capture next to NCCL's watchdog thread is not validated yet
-    if not args.no_graph and world == 1:
+    if not args.no_graph and (world == 1 or args.graph_multi):
         from dn_splatter_b200 import _lib as _L0
         from dn_splatter_b200.graph_step import GraphedTrainStep
 

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libdnr_b200.so")
 
 FLAG_ACTIVATED, FLAG_ANTIALIASED, FLAG_NORMALS, FLAG_ACCUMULATE, FLAG_EXACT_LISTS = 1, 2, 4, 8, 16
 FLAG_HOST_CAMERA = 32
+FLAG_COMPACT_BWD = 64
 REC_FLOATS, REC_FLOATS_N, GRAD_FLOATS = 12, 16, 16
 DEPTH_LOSS_TYPES = {None: 0, "EdgeAwareLogL1": 1, "LogL1": 2, "L1": 3, "MSE": 4}
 
@@ -39,6 +40,7 @@ class DnrArgs(C.Structure):
         ("gt_depth", _p), ("gt_normal", _p), ("gt_rgb", _p), ("loss_partials", _p), ("v_loss", _p),
         ("depth_lambda", _f), ("depth_tolerance", _f), ("depth_loss_type", _i), ("use_normal_loss", _i),
         ("host_cam", _f * 32),
+        ("depth_order", _p),
     ]
 
 
@@ -115,6 +117,8 @@ def load():
     lib.dnr_l1_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dnr_u8_to_f32.restype = C.c_int
     lib.dnr_u8_to_f32.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    lib.dnr_depth_order_ptr.restype = C.c_void_p
+    lib.dnr_depth_order_ptr.argtypes = [C.c_void_p, C.c_int32]
     lib.dnr_bin_scan_workspace_bytes.restype = C.c_size_t
     lib.dnr_bin_scan_workspace_bytes.argtypes = [C.c_int32]
     lib.dnr_bin_sort_workspace_bytes.restype = C.c_size_t
@@ -125,7 +129,7 @@ def load():
 
 EXPORTS = (
     "dnr_version", "dnr_error_string", "dnr_project_fwd", "dnr_bin_scan_workspace_bytes", "dnr_bin_scan",
-    "dnr_bin_sort_workspace_bytes", "dnr_bin_sort", "dnr_raster_fwd", "dnr_finalize_fwd", "dnr_normal_from_depth",
+    "dnr_bin_sort_workspace_bytes", "dnr_bin_sort", "dnr_depth_order_ptr", "dnr_raster_fwd", "dnr_finalize_fwd", "dnr_normal_from_depth",
     "dnr_raster_bwd", "dnr_project_bwd", "dnr_loss_fwd", "dnr_loss_bwd", "dnr_scale_loss_fwd", "dnr_scale_loss_bwd",
     "dnr_l1_fwd", "dnr_l1_bwd", "dnr_u8_to_f32",
 )

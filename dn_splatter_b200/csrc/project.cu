@@ -356,17 +356,23 @@ constexpr int PB_REST_MAX = 45;    // (16 - 1) * 3 floats of higher-order SH gra
 
 // The 180 B/Gaussian SH-gradient rows are staged in shared memory (stride 45 words: conflict-free) and written
 // by the whole CTA as one contiguous, coalesced stream instead of 45 strided 4-byte stores per thread.
-template <bool NORMALS>
+// COMPACT (experimental, DNR_FLAG_COMPACT_BWD): slot s of the grid handles Gaussian depth_order[s]; the visible ones
+// come first in that order, so full CTAs do useful work and the tail CTAs leave after one load.  Rows are then
+// scattered, hence accumulate-only.
+template <bool NORMALS, bool COMPACT>
 __global__ void __launch_bounds__(PB_THREADS, 8) project_bwd_kernel(const DnrArgs a) {
   __shared__ float s_rest[PB_THREADS * PB_REST_MAX];
   __shared__ unsigned char s_vis[PB_THREADS];
   __shared__ unsigned char s_list[PB_THREADS];
+  __shared__ int s_gid[COMPACT ? PB_THREADS : 1];
   __shared__ int s_nvis;
-  const int i = blockIdx.x * PB_THREADS + threadIdx.x;
-  const bool acc = (a.flags & DNR_FLAG_ACCUMULATE) != 0;
+  const int slot = blockIdx.x * PB_THREADS + threadIdx.x;
+  const bool in_range = slot < a.n_gauss;
+  const int i = COMPACT ? (in_range ? a.depth_order[slot] : 0) : slot;  // Gaussian id
+  if (COMPACT) s_gid[threadIdx.x] = i;
+  const bool acc = COMPACT ? true : (a.flags & DNR_FLAG_ACCUMULATE) != 0;
   const int nrest = a.sh_bases - 1;
   const int nrow = nrest * 3;
-  const bool in_range = i < a.n_gauss;
   const int radius = in_range ? a.radii[i] : 0;
   const bool visible = radius > 0;
   s_vis[threadIdx.x] = visible ? 1 : 0;
@@ -612,7 +618,8 @@ __global__ void __launch_bounds__(PB_THREADS, 8) project_bwd_kernel(const DnrArg
       const int total = s_nvis * nrow;
       for (int e = threadIdx.x; e < total; e += PB_THREADS) {
         const int r = s_list[e / nrow], k = e % nrow;
-        out[(size_t)r * nrow + k] += s_rest[r * PB_REST_MAX + k];
+        if (COMPACT) a.v_sh_rest[(size_t)s_gid[r] * nrow + k] += s_rest[r * PB_REST_MAX + k];
+        else out[(size_t)r * nrow + k] += s_rest[r * PB_REST_MAX + k];
       }
     }
   }
@@ -656,8 +663,15 @@ extern "C" int dnr_project_bwd(const DnrArgs* a, void* stream) {
   if (a->sh_bases > 16) return DNR_E_OPTION;
   const int block = PB_THREADS, grid = (a->n_gauss + block - 1) / block;
   cudaStream_t s = (cudaStream_t)stream;
-  if (normals) project_bwd_kernel<true><<<grid, block, 0, s>>>(*a);
-  else project_bwd_kernel<false><<<grid, block, 0, s>>>(*a);
+  if (a->flags & DNR_FLAG_COMPACT_BWD) {
+    if (!a->depth_order) return DNR_E_NULL;
+    if (!(a->flags & DNR_FLAG_ACCUMULATE)) return DNR_E_OPTION;  // scattered rows: the caller pre-zeroes and accumulates
+    if (normals) project_bwd_kernel<true, true><<<grid, block, 0, s>>>(*a);
+    else project_bwd_kernel<false, true><<<grid, block, 0, s>>>(*a);
+  } else {
+    if (normals) project_bwd_kernel<true, false><<<grid, block, 0, s>>>(*a);
+    else project_bwd_kernel<false, false><<<grid, block, 0, s>>>(*a);
+  }
   DNR_CHECK_LAUNCH();
   return 0;
 }

@@ -128,6 +128,7 @@ class RasterSettings:
     exact_lists: bool = False  # parity mode: gsplat's full bbox intersection lists instead of the precise-hit lists
     sync_free: bool = False  # size the intersection buffers from past views instead of reading the count back
     fixed_capacity: int = 0  # > 0: use exactly this many intersection slots, no host bookkeeping (CUDA-graph capture)
+    compact_bwd: bool = False  # EXPERIMENTAL (not GPU-validated yet): project_bwd over visible Gaussians only
 
 
 class RasterOutput(NamedTuple):
@@ -301,6 +302,7 @@ class _DnRasterize(torch.autograd.Function):
 
         ctx.settings, ctx.n, ctx.sh_bases, ctx.n_isects, ctx.host_cam = s, n, sh_bases, n_isects, host_cam
         ctx.save_for_backward(means, quats, scales, opac, sh_dc, sh_rest, viewmat, K, c2w if s.render_normals else None)
+        ctx.ws_scan = ws_scan if s.compact_bwd else None
         ctx.state = dict(radii=radii, records=records, flatten_ids=flatten_ids, tile_offsets=tile_offsets,
                          out_depth=out_depth, out_alpha=out_alpha, out_normal=out_normal, last_ids=last_ids,
                          normal_norm=normal_norm, clamp_mask=clamp_mask, means2d=means2d)
@@ -351,18 +353,24 @@ class _DnRasterize(torch.autograd.Function):
              v_normal=v_normal, v_alpha=v_alpha, grad_records=grad_records)
         L.check(_timed("raster_bwd", lib.dnr_raster_bwd, C.byref(a), st), "dnr_raster_bwd")
         sink = ctx.grad_sink
+        if s.compact_bwd:
+            a.flags |= L.FLAG_COMPACT_BWD
+            a.depth_order = lib.dnr_depth_order_ptr(ctx.ws_scan.data_ptr(), n)
         if sink is not None:
             # write straight into the caller's (pre-zeroed, e.g. flat all-reduce bucket) gradient buffers
             a.flags |= L.FLAG_ACCUMULATE
             v_means, v_quats, v_scales = sink["means"], sink["quats"], sink["scales"]
             v_opac, v_sh_dc, v_sh_rest = sink["opacities"], sink["features_dc"], sink["features_rest"]
         else:
-            v_means = torch.empty_like(means)
-            v_quats = torch.empty_like(quats)
-            v_scales = torch.empty_like(scales)
-            v_opac = torch.empty_like(opac)
-            v_sh_dc = torch.empty_like(sh_dc)
-            v_sh_rest = torch.empty_like(sh_rest)
+            alloc = torch.zeros_like if s.compact_bwd else torch.empty_like  # the compact kernel only accumulates
+            if s.compact_bwd:
+                a.flags |= L.FLAG_ACCUMULATE
+            v_means = alloc(means)
+            v_quats = alloc(quats)
+            v_scales = alloc(scales)
+            v_opac = alloc(opac)
+            v_sh_dc = alloc(sh_dc)
+            v_sh_rest = alloc(sh_rest)
         v_m2d = torch.empty(n, 2, **f32)
         v_m2d_abs = torch.empty(n, 2, **f32)
         _set(a, v_means=v_means, v_quats=v_quats, v_scales=v_scales, v_opacities=v_opac, v_sh_dc=v_sh_dc,
@@ -382,7 +390,7 @@ def dn_rasterize(
     far_plane: float = 1e10, eps2d: float = 0.3, antialiased: bool = False,
     background: Sequence[float] = (0.0, 0.0, 0.0), render_normals: bool = True, c2w: Optional[Tensor] = None,
     activated: bool = False, surface_normal: bool = True, grad_sink: Optional[dict] = None,
-    exact_lists: bool = False, sync_free: bool = False, fixed_capacity: int = 0,
+    exact_lists: bool = False, sync_free: bool = False, fixed_capacity: int = 0, compact_bwd: bool = False,
 ) -> RasterOutput:
     """Renders one view.  Inputs are the reference's RAW gauss_params (log-scales, opacity logits,
     un-normalised wxyz quats, SH coefficients split as features_dc / features_rest) unless
@@ -394,7 +402,7 @@ def dn_rasterize(
     settings = RasterSettings(width=int(width), height=int(height), sh_degree=int(sh_degree), near_plane=near_plane,
                               far_plane=far_plane, eps2d=eps2d, antialiased=antialiased, render_normals=render_normals,
                               activated=activated, background=bg, surface_normal=surface_normal, exact_lists=exact_lists,
-                              sync_free=sync_free, fixed_capacity=int(fixed_capacity))
+                              sync_free=sync_free, fixed_capacity=int(fixed_capacity), compact_bwd=compact_bwd)
     info: dict = {}
     if grad_sink is not None:
         # dict with fp32 contiguous buffers shaped like the six parameters (keys: means, quats, scales, opacities,

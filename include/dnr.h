@@ -49,6 +49,8 @@ extern "C" {
 #define DNR_FLAG_ANTIALIASED 2u /* rasterize_mode == "antialiased": opacity *= compensation */
 #define DNR_FLAG_NORMALS 4u     /* predict_normals: render the per-Gaussian normal channels */
 #define DNR_FLAG_ACCUMULATE 8u  /* project_bwd adds into the parameter-gradient buffers */
+#define DNR_FLAG_COMPACT_BWD 64u /* EXPERIMENTAL (not validated on a GPU yet): project_bwd walks the depth-sorted index
+                                    (a->depth_order), so only visible Gaussians occupy lanes; needs DNR_FLAG_ACCUMULATE */
 #define DNR_FLAG_HOST_CAMERA 32u /* camera passed by value in host_cam[] (no device reads, no H2D copy) */
 #define DNR_FLAG_EXACT_LISTS 16u /* parity mode: emit gsplat's full bbox intersection lists (no precise-hit cull) */
 
@@ -147,6 +149,7 @@ typedef struct DnrArgs {
   int32_t use_normal_loss;
   /* with DNR_FLAG_HOST_CAMERA: [0..15] viewmat, [16..19] fx fy cx cy, [20..31] c2w[3,4]; viewmat/K/c2w pointers unused */
   float host_cam[32];
+  const int32_t* depth_order; /* [N] Gaussian ids sorted by depth, visible first (dnr_depth_order_ptr); COMPACT_BWD only */
 } DnrArgs;
 
 int dnr_version(void);
@@ -161,6 +164,8 @@ size_t dnr_bin_scan_workspace_bytes(int32_t n_gauss);
  * pass NULL to stay asynchronous and size by capacity. */
 int dnr_bin_scan(const DnrArgs* a, void* stream, int64_t* n_isects_host);
 size_t dnr_bin_sort_workspace_bytes(int32_t n_gauss, int64_t n_isects, int32_t n_tiles);
+/* Device pointer to the depth-sorted Gaussian ids inside a bin_scan workspace (valid after dnr_bin_scan). */
+const int32_t* dnr_depth_order_ptr(void* ws_scan, int32_t n_gauss);
 int dnr_bin_sort(const DnrArgs* a, void* stream);
 
 int dnr_raster_fwd(const DnrArgs* a, void* stream);

@@ -184,3 +184,19 @@ def test_sync_free_capacity_mode_matches_sync_mode():
     for k in p:  # same kernels, same lists: only the order of the float atomics differs between two runs
         rel = float((p[k].grad - pr[k].grad).norm() / (pr[k].grad.norm() + 1e-30))
         assert rel < 1e-4, (k, rel)
+
+
+@needs_cuda
+@pytest.mark.skipif(__import__("os").environ.get("DNR_TEST_EXPERIMENTAL") != "1", reason="experimental kernels: opt-in")
+@pytest.mark.parametrize("case", CASES[:2])
+def test_experimental_compact_project_bwd_matches_default(case):
+    """DNR_FLAG_COMPACT_BWD (round-2 candidate) must give the default backward's gradients."""
+    params, cam = scene_and_camera(**case)
+    pa, a = cuda_outputs(params, cam, requires_grad=True)
+    pb, b = cuda_outputs(params, cam, requires_grad=True, compact_bwd=True)
+    _loss(a.rgb, a.depth, a.normal, a.alpha).backward()
+    _loss(b.rgb, b.depth, b.normal, b.alpha).backward()
+    for k in pa:
+        rel = float((pa[k].grad - pb[k].grad).norm() / (pa[k].grad.norm() + 1e-30))
+        assert rel < 1e-4, (k, rel)
+    assert float((a.means2d.absgrad - b.means2d.absgrad).abs().max()) < 1e-4 * float(a.means2d.absgrad.abs().max() + 1e-30)

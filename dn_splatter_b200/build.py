@@ -23,6 +23,7 @@ SOURCES = {
     "binning.cu": [],
     "raster.cu": [],
     "misc.cu": [],
+    "ssim.cu": [],
 }
 
 

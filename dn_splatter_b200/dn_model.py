@@ -21,7 +21,7 @@ from torch import Tensor
 from .cameras import Cameras, is_camera
 from .losses import DepthLoss, DepthLossType, TVLoss
 from .rasterize import dn_rasterize, get_viewmat, to_device_async
-from .regularization_strategy import AGSMeshRegularization, DNRegularization, FusedL1, u8_to_float
+from .regularization_strategy import AGSMeshRegularization, DNRegularization, FusedL1, FusedSSIM, u8_to_float
 from .utils.normal_utils import normal_from_depth_image
 
 SH_C0 = 0.28209479177387814
@@ -148,6 +148,8 @@ class DNSplatterModelConfig:
     """Emit gsplat's full bbox tile lists instead of the precise-hit lists (parity debugging; images are identical)."""
     sync_free: bool = False
     """Size intersection buffers from earlier views instead of reading the count back (no host sync per view)."""
+    fused_ssim: bool = False
+    """EXPERIMENTAL (round 1, not yet GPU-validated): evaluate the SSIM term with csrc/ssim.cu instead of torch convs."""
 
     def setup(self, **kwargs):
         return self._target(self, **kwargs)
@@ -466,7 +468,11 @@ class DNSplatterModel(torch.nn.Module):
             l1 = torch.abs(gt_img - pred_img).mean()
         main = (1 - cfg.ssim_lambda) * l1
         if cfg.ssim_lambda > 0:
-            main = main + cfg.ssim_lambda * (1 - ssim(gt_img.permute(2, 0, 1)[None], pred_img.permute(2, 0, 1)[None]))
+            if cfg.fused_ssim and pred_img.is_cuda:
+                sim = FusedSSIM.apply(pred_img, gt_img)
+            else:
+                sim = ssim(gt_img.permute(2, 0, 1)[None], pred_img.permute(2, 0, 1)[None])
+            main = main + cfg.ssim_lambda * (1 - sim)
         if cfg.use_scale_regularization and self.step % 10 == 0:
             se = torch.exp(self.scales)
             reg = torch.clamp(se.amax(dim=-1) / se.amin(dim=-1), min=cfg.max_gauss_ratio) - cfg.max_gauss_ratio

@@ -157,6 +157,41 @@ class FusedL1(torch.autograd.Function):
         return vp.view(ctx.shape), None
 
 
+class FusedSSIM(torch.autograd.Function):
+    """Mean SSIM of two [H,W,C] fp32 CUDA images (torchmetrics semantics, see dn_model.ssim) in one kernel each way;
+    differentiable w.r.t. `pred` only.  EXPERIMENTAL in round 1: enabled by DNSplatterModelConfig.fused_ssim; the torch
+    implementation dn_model.ssim() is its reference (tests/test_gpu_model.py::test_fused_ssim_matches_torch)."""
+
+    @staticmethod
+    def forward(ctx, pred, gt):
+        lib = L.load()
+        if pred.device.type != "cuda" or gt.device != pred.device:
+            raise L.DnrError("FusedSSIM needs CUDA tensors on one device (no CPU path)")
+        p = pred.detach().float().contiguous()
+        g = gt.detach().float().contiguous()
+        assert p.dim() == 3 and p.shape == g.shape, "pred / gt must both be [H,W,C]"
+        H, W, Cn = p.shape
+        dmaps = torch.empty((3, H, W, Cn), dtype=torch.float32, device=p.device)
+        out = torch.empty(1, dtype=torch.float32, device=p.device)
+        L.check(lib.dnr_ssim_fwd(p.data_ptr(), g.data_ptr(), H, W, Cn, dmaps.data_ptr(), out.data_ptr(), _stream()),
+                "dnr_ssim_fwd")
+        ctx.keep = (p, g, dmaps)
+        ctx.fwd_stream = torch.cuda.current_stream()
+        return out[0] / float((H - 10) * (W - 10) * Cn)
+
+    @staticmethod
+    def backward(ctx, v):
+        with torch.cuda.stream(ctx.fwd_stream):
+            lib = L.load()
+            p, g, dmaps = ctx.keep
+            v = v.detach().float().contiguous()
+            vp = torch.empty_like(p)
+            H, W, Cn = p.shape
+            L.check(lib.dnr_ssim_bwd(p.data_ptr(), g.data_ptr(), H, W, Cn, dmaps.data_ptr(), v.data_ptr(), vp.data_ptr(),
+                                     _stream()), "dnr_ssim_bwd")
+            return vp, None
+
+
 def u8_to_float(img: Tensor, divisor: float = 255.0, clamp_min: float = 0.0) -> Tensor:
     """uint8 CUDA image -> fp32 (/divisor, clamped from below) in one kernel (get_gt_img + clamp of the reference)."""
     src = img.contiguous()

@@ -200,6 +200,17 @@ int dnr_l1_bwd(const float* pred, const void* gt, int64_t n, int32_t gt_is_u8, c
 /* get_gt_img's uint8 -> float conversion in one pass: dst[i] = max(src[i] / divisor, clamp_min). */
 int dnr_u8_to_f32(const uint8_t* src, int64_t n, float divisor, float clamp_min, float* dst, void* stream);
 
+/* SSIM term of the same photometric loss: torchmetrics StructuralSimilarityIndexMeasure(data_range=1.0,
+ * kernel_size=11) (dn_splatter/dn_model.py:180), i.e. an 11x11 Gaussian window (sigma 1.5), mean over the
+ * (H-10)x(W-10) interior.  pred / gt: [H,W,C] fp32.  fwd: *sum_out (zeroed by the call) = SUM of the SSIM map over
+ * the interior and all channels (divide by (H-10)(W-10)C for the mean); dmaps [3,H,W,C] keeps the partial
+ * derivatives for the backward.  bwd: v_pred[H,W,C] = (*v_mean or 1) * d(mean SSIM)/d(pred).
+ * EXPERIMENTAL in round 1 (written after the GPU budget was spent; opt-in through fused_ssim). */
+int dnr_ssim_fwd(const float* pred, const float* gt, int32_t H, int32_t W, int32_t C, float* dmaps, float* sum_out,
+                 void* stream);
+int dnr_ssim_bwd(const float* pred, const float* gt, int32_t H, int32_t W, int32_t C, const float* dmaps,
+                 const float* v_mean, float* v_pred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -220,3 +220,27 @@ def _graph_step_body():
         assert abs(float(loss) - eager[i][0]) <= 1e-5 * max(1.0, abs(eager[i][0])), (i, float(loss), eager[i][0])
         rel = float((bucket.flat - eager[i][1]).norm() / (eager[i][1].norm() + 1e-30))
         assert rel < 1e-4, (i, rel)
+
+
+@needs_cuda
+@pytest.mark.skipif(__import__("os").environ.get("DNR_TEST_EXPERIMENTAL") != "1", reason="experimental kernels: opt-in")
+@pytest.mark.parametrize("hw", [(64, 80), (37, 53), (128, 160), (11, 200)])
+def test_fused_ssim_matches_torch(hw):
+    """csrc/ssim.cu (value + gradient) against dn_model.ssim() — the torchmetrics restatement the default path uses."""
+    from dn_splatter_b200.dn_model import ssim
+    from dn_splatter_b200.regularization_strategy import FusedSSIM
+
+    H, W = hw
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    x = torch.rand(H, W, 3, generator=g).cuda().requires_grad_(True)
+    y = (x.detach().cpu() * 0.6 + 0.4 * torch.rand(H, W, 3, generator=g)).cuda()
+    if H <= 10 or W <= 10:
+        with pytest.raises(Exception):
+            FusedSSIM.apply(x, y)
+        return
+    ref = ssim(y.permute(2, 0, 1)[None], x.permute(2, 0, 1)[None])
+    (gref,) = torch.autograd.grad(ref, x)
+    out = FusedSSIM.apply(x, y)
+    (gout,) = torch.autograd.grad(out, x)
+    assert abs(float(out) - float(ref)) < 2e-5
+    assert float((gout - gref).norm() / gref.norm()) < 1e-4

@@ -24,6 +24,7 @@ SOURCES = {
     "raster.cu": [],
     "misc.cu": [],
     "ssim.cu": [],
+    "adam.cu": ["-fmad=false"],
 }
 
 

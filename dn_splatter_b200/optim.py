@@ -1,0 +1,101 @@
+"""One-launch Adam for the Gaussian parameter groups.
+
+The reference creates one torch.optim.Adam per parameter group (/root/reference/dn_splatter/dn_config.py:29-68: a
+learning rate per group, eps 1e-15, an exponential schedule on `means`) and nerfstudio steps them in turn.
+`FusedAdam` keeps that surface — it IS a torch.optim.Optimizer with one param_group per Gaussian group and the usual
+`state[p] = {"step", "exp_avg", "exp_avg_sq"}`, so densification's moment surgery (densify._resize_adam_state) and
+checkpointing work unchanged — but `step()` is a single `dnr_adam_step` launch over all groups.
+
+EXPERIMENTAL in round 1: the update rule is pinned against torch.optim.Adam on the CPU through
+`reference_step` (tests/test_fused_adam_cpu.py); the kernel has not run on a GPU yet
+(opt-in test: DNR_TEST_EXPERIMENTAL=1 pytest -m gpu -k fused_adam).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Iterable, Optional
+
+import torch
+
+from . import _lib as L
+
+
+def bias_corrections(step: int, beta1: float, beta2: float):
+    """(1 - beta1^t, sqrt(1 - beta2^t)) in double precision, as torch's Adam computes them on the host."""
+    return 1.0 - beta1 ** step, math.sqrt(1.0 - beta2 ** step)
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """Adam (no weight decay, no amsgrad) over several parameter groups in one kernel launch.
+
+    `params`: an iterable of param_group dicts `{"params": [p], "lr": ..., "eps": ..., "name": ...}`; use
+    `FusedAdam.for_model(model)` to build the reference's groups."""
+
+    def __init__(self, params: Iterable[Dict], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-15):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        n = sum(len(g["params"]) for g in self.param_groups)
+        if n > 16:
+            raise ValueError("FusedAdam handles at most 16 tensors per launch (DNR_ADAM_MAX_SEGS)")
+
+    @classmethod
+    def for_model(cls, model, groups: Optional[Dict[str, Dict]] = None) -> "FusedAdam":
+        from .dn_config import optimizer_groups
+
+        groups = groups or optimizer_groups()
+        pg = [{"params": [p], "lr": groups[name]["lr"], "eps": groups[name]["eps"], "name": name}
+              for name, p in model.gauss_params.items() if name in groups]
+        return cls(pg)
+
+    def as_dict(self, model) -> Dict[str, "FusedAdam"]:
+        """The `{group name: optimizer}` mapping densify.refinement_after expects (every name -> this optimizer)."""
+        return {g["name"]: self for g in self.param_groups if "name" in g}
+
+    def _segments(self):
+        segs = []
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["step"] = int(st["step"]) + 1
+                bc1, bc2s = bias_corrections(st["step"], b1, b2)
+                segs.append((p, p.grad, st["exp_avg"], st["exp_avg_sq"], float(group["lr"]), float(group["eps"]), bc1, bc2s,
+                             b1, b2))
+        return segs
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        segs = self._segments()
+        if not segs:
+            return loss
+        if not all(s[0].is_cuda for s in segs):
+            raise L.DnrError("FusedAdam needs CUDA parameters (no CPU path)")
+        b1, b2 = segs[0][8], segs[0][9]
+        assert all(s[8] == b1 and s[9] == b2 for s in segs), "one (beta1, beta2) pair per launch"
+        arr = (L.DnrAdamSeg * len(segs))()
+        for i, (p, g, m, v, lr, eps, bc1, bc2s, _, _) in enumerate(segs):
+            assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+            assert p.dtype == g.dtype == torch.float32
+            arr[i].p, arr[i].g, arr[i].m, arr[i].v = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
+            arr[i].n, arr[i].lr, arr[i].eps, arr[i].bc1, arr[i].bc2_sqrt = p.numel(), lr, eps, bc1, bc2s
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L.check(L.load().dnr_adam_step(ctypes.cast(arr, ctypes.c_void_p), len(segs), b1, b2, stream), "dnr_adam_step")
+        return loss
+
+    @torch.no_grad()
+    def reference_step(self):
+        """The kernel's arithmetic restated in torch, operation for operation (csrc/adam.cu: adam_one) — used ONLY by the
+        CPU test that pins the update rule against torch.optim.Adam; never called by the product path."""
+        for (p, g, m, v, lr, eps, bc1, bc2s, b1, b2) in self._segments():
+            f = lambda x: torch.tensor(x, dtype=torch.float32)
+            m.copy_(m + f(1.0 - b1) * (g - m))
+            v.copy_(f(b2) * v + f(1.0 - b2) * g * g)
+            denom = v.sqrt() / f(bc2s) + f(eps)
+            p.copy_(p - f(lr / bc1) * (m / denom))

@@ -24,7 +24,7 @@ class FlatGradBucket:
     def __init__(self, params: Dict[str, torch.nn.Parameter], names: Iterable[str] = GRAD_PARAMS):
         self.names = [n for n in names if n in params]
         self.params = {n: params[n] for n in self.names}
-        total = sum(p.numel() for p in self.params.values())
+        total = sum(self._padded(p.numel()) for p in self.params.values())
         dev = next(iter(self.params.values())).device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.views: Dict[str, Tensor] = {}
@@ -33,7 +33,12 @@ class FlatGradBucket:
             v = self.flat[off:off + p.numel()].view_as(p)
             p.grad = v
             self.views[n] = v
-            off += p.numel()
+            off += self._padded(p.numel())
+
+    @staticmethod
+    def _padded(n: int) -> int:
+        """Segments start on 16-byte boundaries (float4 access in dnr_adam_step; the padding floats stay zero)."""
+        return (n + 3) & ~3
 
     def zero_(self) -> None:
         self.flat.zero_()

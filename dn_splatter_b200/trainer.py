@@ -15,10 +15,17 @@ from .dn_config import MAX_NUM_ITERATIONS, optimizer_groups
 
 class Trainer:
     def __init__(self, model, next_train: Callable[[int], tuple], max_steps: int = MAX_NUM_ITERATIONS,
-                 world_size: int = 1, seed: int = 0):
+                 world_size: int = 1, seed: int = 0, fused_adam: bool = False):
         self.model, self.next_train, self.max_steps = model, next_train, max_steps
         self.groups = optimizer_groups(max_steps)
-        self.optimizers: Dict[str, torch.optim.Optimizer] = build_optimizers(model, self.groups)
+        self.fused = None
+        if fused_adam:  # EXPERIMENTAL (round 1): all groups in one dnr_adam_step launch, see optim.py
+            from .optim import FusedAdam
+
+            self.fused = FusedAdam.for_model(model, self.groups)
+            self.optimizers: Dict[str, torch.optim.Optimizer] = self.fused.as_dict(model)
+        else:
+            self.optimizers = build_optimizers(model, self.groups)
         self.bucket = model.enable_flat_grads()
         self.world_size = world_size
         self.generator = torch.Generator().manual_seed(seed)  # identical on every rank: identical split samples
@@ -41,8 +48,12 @@ class Trainer:
             g = self.groups[name]
             if g.get("lr_final"):
                 for pg in opt.param_groups:
-                    pg["lr"] = exponential_lr(g["lr"], g["lr_final"], step, g["max_steps"])
-            opt.step()
+                    if pg.get("name", name) == name:
+                        pg["lr"] = exponential_lr(g["lr"], g["lr_final"], step, g["max_steps"])
+            if self.fused is None:
+                opt.step()
+        if self.fused is not None:
+            self.fused.step()
         m.after_train(step)
         info: Optional[Dict[str, int]] = None
         if step > 0 and step % m.config.refine_every == 0:

@@ -211,6 +211,21 @@ int dnr_ssim_fwd(const float* pred, const float* gt, int32_t H, int32_t W, int32
 int dnr_ssim_bwd(const float* pred, const float* gt, int32_t H, int32_t W, int32_t C, const float* dmaps,
                  const float* v_mean, float* v_pred, void* stream);
 
+/* One-launch Adam over all Gaussian parameter groups: replaces the per-group torch.optim.Adam instances of
+ * dn_splatter/dn_config.py:29-68 (lr per group, eps 1e-15; betas (0.9, 0.999), no weight decay, no amsgrad).
+ * bc1 = 1 - beta1^t and bc2_sqrt = sqrt(1 - beta2^t) are computed by the host for each group's own step count t.
+ * EXPERIMENTAL in round 1 (opt-in through optim.FusedAdam). */
+#define DNR_ADAM_MAX_SEGS 16
+typedef struct DnrAdamSeg {
+  float* p;       /* [n] parameters, updated in place */
+  const float* g; /* [n] gradients */
+  float* m;       /* [n] exp_avg, updated in place */
+  float* v;       /* [n] exp_avg_sq, updated in place */
+  int64_t n;
+  double lr, eps, bc1, bc2_sqrt; /* doubles: rounded to fp32 exactly where torch.optim.Adam rounds them */
+} DnrAdamSeg;
+int dnr_adam_step(const DnrAdamSeg* segs /* HOST array */, int32_t n_segs, double beta1, double beta2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

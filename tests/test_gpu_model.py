@@ -244,3 +244,30 @@ def test_fused_ssim_matches_torch(hw):
     (gout,) = torch.autograd.grad(out, x)
     assert abs(float(out) - float(ref)) < 2e-5
     assert float((gout - gref).norm() / gref.norm()) < 1e-4
+
+
+@needs_cuda
+@pytest.mark.skipif(__import__("os").environ.get("DNR_TEST_EXPERIMENTAL") != "1", reason="experimental kernels: opt-in")
+def test_fused_adam_matches_torch_adam():
+    """optim.FusedAdam (one dnr_adam_step launch) against one torch.optim.Adam per group over 20 steps, odd sizes
+    (scalar tail, unaligned views) included."""
+    from dn_splatter_b200.optim import FusedAdam
+
+    g = torch.Generator().manual_seed(11)
+    shapes = {"means": (1001, 3), "quats": (1001, 4), "features_rest": (1001, 15, 3), "opacities": (1001, 1), "odd": (7,)}
+    lrs = {"means": 1.6e-4, "quats": 1e-3, "features_rest": 1.25e-4, "opacities": 5e-2, "odd": 1e-2}
+    a = {k: torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for k, s in shapes.items()}
+    b = {k: torch.nn.Parameter(v.detach().clone()) for k, v in a.items()}
+    fused = FusedAdam([{"params": [p], "lr": lrs[k], "eps": 1e-15, "name": k} for k, p in a.items()])
+    ref = {k: torch.optim.Adam([p], lr=lrs[k], eps=1e-15) for k, p in b.items()}
+    for step in range(20):
+        for k in a:
+            grad = (torch.randn(shapes[k], generator=g) * 10.0 ** (-(len(k) % 5))).cuda()
+            a[k].grad, b[k].grad = grad.clone(), grad.clone()
+        fused.step()
+        for o in ref.values():
+            o.step()
+    for k in a:
+        for x, y in ((fused.state[a[k]]["exp_avg"], ref[k].state[b[k]]["exp_avg"]),
+                     (fused.state[a[k]]["exp_avg_sq"], ref[k].state[b[k]]["exp_avg_sq"]), (a[k].data, b[k].data)):
+            assert float((x - y).abs().max()) <= 1e-5 * float(y.abs().max()), k

@@ -64,4 +64,4 @@ def test_training_loop_reduces_loss_and_densifies():
         assert p.shape[0] == n and opt.param_groups[0]["params"][0] is p
         st = opt.state.get(p)
         assert st is None or st["exp_avg"].shape == p.shape
-    assert model._bucket is not None and model._bucket.flat.numel() == n * 59
+    assert model._bucket is not None and n * 59 <= model._bucket.flat.numel() < n * 59 + 24

@@ -58,4 +58,4 @@ def test_trainer_fits_a_small_scene_and_survives_refinement():
     for name, opt in tr.optimizers.items():
         p = model.gauss_params[name]
         assert p.shape[0] == n and opt.param_groups[0]["params"][0] is p
-    assert model._bucket.flat.numel() == n * 59
+    assert n * 59 <= model._bucket.flat.numel() < n * 59 + 24  # segments padded to 16 B

@@ -161,6 +161,10 @@ def _require_cuda(*ts: Tensor) -> torch.device:
     for t in ts:
         if t is not None and t.device != dev:
             raise L.DnrError("all tensors must live on the same CUDA device")
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        # kernels are enqueued on torch's CURRENT stream, which belongs to the current device
+        raise L.DnrError(f"tensors are on {dev} but the current device is cuda:{torch.cuda.current_device()}: "
+                         "call torch.cuda.set_device / use torch.cuda.device(...)")
     return dev
 
 

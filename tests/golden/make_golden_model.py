@@ -220,7 +220,8 @@ def make_model(M, params, background, **cfg_kw):
     # the wiring of populate_modules (dn_model.py:224-265), by hand: populate_modules itself needs seed points,
     # a CameraOptimizer and the parent's populate_modules
     m.depth_loss = DepthLoss(cfg.depth_loss_type)
-    m.regularization_strategy = M.DNRegularization()
+    m.regularization_strategy = (M.DNRegularization() if cfg.regularization_strategy == "dn-splatter"
+                                 else M.AGSMeshRegularization())
     if cfg.use_depth_loss:
         m.regularization_strategy.depth_loss_type = cfg.depth_loss_type
         m.regularization_strategy.depth_loss = m.depth_loss
@@ -249,6 +250,9 @@ def main():
                            normal_supervision="depth", use_scale_regularization=True)),
         "c": dict(n=300, W=48, H=48, view=0, mask=False, depth_key=None,
                   cfg=dict(use_depth_loss=False, predict_normals=True, normal_supervision="mono")),
+        "d": dict(n=300, W=48, H=40, view=2, mask=False, depth_key="sensor_depth", confidence=True,
+                  cfg=dict(use_depth_loss=True, depth_lambda=0.2, depth_loss_type=DepthLossType.EdgeAwareLogL1,
+                           normal_supervision="mono", regularization_strategy="ags-mesh")),
     }
     for tag, c in cases.items():
         params = make_scene(c["n"], seed=7 + ord(tag))
@@ -260,6 +264,8 @@ def main():
             d = 2 + 6 * torch.rand(H, W, 1, generator=g)
             d[torch.rand(H, W, 1, generator=g) < 0.1] = 0.0
             batch[c["depth_key"]] = d
+        if c.get("confidence"):
+            batch["confidence"] = (torch.rand(H, W, 1, generator=g) * 255).to(torch.uint8)
         if c["mask"]:
             batch["mask"] = (torch.rand(H, W, 1, generator=g) > 0.2).float()
         bg = torch.tensor(BACKGROUND)

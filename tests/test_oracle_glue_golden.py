@@ -46,7 +46,7 @@ def model_from_golden(z, device="cpu"):
 
 
 def test_goldens_exist():
-    assert len(FILES) == 3
+    assert len(FILES) == 4
 
 
 @pytest.mark.parametrize("f", FILES, ids=[os.path.basename(f) for f in FILES])

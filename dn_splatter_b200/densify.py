@@ -137,9 +137,12 @@ def refinement_after(model, optimizers: Dict[str, torch.optim.Optimizer], step: 
         if step < cfg.stop_screen_size_at:
             splits |= state.max_2Dsize > cfg.split_screen_size
         splits &= high
-        dups = (~big) & high
         data = {k: gp[k].data for k in names}
         new_split = split_gaussians(data, splits, cfg.n_split_samples, cfg.split_size_factor, generator)
+        # the reference takes the dup mask AFTER split_gaussians has shrunk the parents in place (dn_model.py:309-316):
+        # a split parent that falls below densify_size_thresh after the /1.6 is duplicated as well (the copy survives,
+        # the parent itself is culled below) — pinned by tests/test_densify_golden.py
+        dups = (data["scales"].exp().max(dim=-1).values <= cfg.densify_size_thresh) & high
         new_dup = dup_gaussians(data, dups)
         n_split, n_dup = int(splits.sum()), int(dups.sum())
         info["split"], info["dup"] = n_split, n_dup

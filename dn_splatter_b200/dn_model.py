@@ -84,7 +84,11 @@ def matrix_to_quaternion(M: Tensor) -> Tensor:
     branch = torch.where(tr > 0, 0, torch.where((m[:, 0, 0] > m[:, 1, 1]) & (m[:, 0, 0] > m[:, 2, 2]), 1,
                                                 torch.where(m[:, 1, 1] > m[:, 2, 2], 2, 3)))
     q = cand[torch.arange(len(m)), branch]
-    return F.normalize(q, dim=-1)
+    # q / S with S = 2 sqrt(d), d the branch's own diagonal term: a unit quaternion for a proper rotation, and — like
+    # the reference, which does not renormalise — (0,0,0,0.7071) for the -I that rotation_between returns for
+    # anti-parallel vectors (pinned by tests/test_init_golden.py)
+    d = q[torch.arange(len(m)), branch]
+    return q / (2.0 * torch.sqrt(d))[:, None]
 
 
 @dataclass

@@ -253,6 +253,14 @@ def main():
         "d": dict(n=300, W=48, H=40, view=2, mask=False, depth_key="sensor_depth", confidence=True,
                   cfg=dict(use_depth_loss=True, depth_lambda=0.2, depth_loss_type=DepthLossType.EdgeAwareLogL1,
                            normal_supervision="mono", regularization_strategy="ags-mesh")),
+        "e": dict(n=300, W=48, H=40, view=4, mask=False, depth_key="mono_depth",
+                  cfg=dict(use_depth_loss=True, depth_lambda=0.2, depth_loss_type=DepthLossType.EdgeAwareLogL1,
+                           normal_supervision="mono", rasterize_mode="antialiased")),
+        "f": dict(n=300, W=48, H=40, view=1, mask=False, depth_key="mono_depth", step=1500,  # SH degree 1 of 3
+                  cfg=dict(use_depth_loss=True, depth_lambda=0.2, depth_loss_type=DepthLossType.L1,
+                           normal_supervision="mono")),
+        "g": dict(n=300, W=48, H=40, view=2, mask=False, depth_key=None, eval=True,  # eval mode, forward only
+                  cfg=dict(use_depth_loss=False, normal_supervision="mono")),
     }
     for tag, c in cases.items():
         params = make_scene(c["n"], seed=7 + ord(tag))
@@ -270,9 +278,14 @@ def main():
             batch["mask"] = (torch.rand(H, W, 1, generator=g) > 0.2).float()
         bg = torch.tensor(BACKGROUND)
         m = make_model(M, params, bg, ssim_lambda=0.0, num_downscales=0, max_gauss_ratio=5.0, **c["cfg"])
+        m.step = c.get("step", 30000)
+        if c.get("eval"):
+            m.eval()
         camera = make_camera(M, cam)
         outputs = M.DNSplatterModel.get_outputs(m, camera)
         saved = {k: outputs[k].detach().clone() for k in ("rgb", "depth", "normal", "surface_normal", "accumulation")}
+        if c.get("eval"):
+            m.train()  # the loss below is only there to keep the file layout uniform
         loss_dict = M.DNSplatterModel.get_loss_dict(m, outputs, {k: v.clone() for k, v in batch.items()})
         total = loss_dict["main_loss"] + loss_dict["scale_reg"]
         total.backward()
@@ -291,6 +304,7 @@ def main():
             z["grad_" + k] = m.gauss_params[k].grad.numpy()
         cfgd = {k: (v.value if hasattr(v, "value") else v) for k, v in c["cfg"].items()}
         z["cfg_json"] = np.array(__import__("json").dumps(cfgd))
+        z["step"], z["eval"] = np.array(c.get("step", 30000)), np.array(bool(c.get("eval", False)))
         np.savez_compressed(os.path.join(OUT, f"dn_model_glue_{tag}.npz"), **z)
         print(tag, "main_loss", float(loss_dict["main_loss"]), "scale_reg", float(loss_dict["scale_reg"]),
               "visible", int((m.radii > 0).sum()), "/", c["n"])

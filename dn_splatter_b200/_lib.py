@@ -51,6 +51,12 @@ class DnrAdamSeg(C.Structure):
                 ("bc1", C.c_double), ("bc2_sqrt", C.c_double)]
 
 
+class DnrKnnGrid(C.Structure):
+    """Mirror of struct DnrKnnGrid (include/dnr.h)."""
+
+    _fields_ = [("lo", _f * 3), ("cell", _f), ("inv_cell", _f), ("dims", C.c_int32 * 3)]
+
+
 POINTER_FIELDS = {n for n, t in DnrArgs._fields_ if t is _p}
 
 _lib: Optional[C.CDLL] = None
@@ -62,6 +68,7 @@ KERNELS_PER_CALL = {
     "dnr_loss_fwd": (2, 0), "dnr_loss_bwd": (1, 0), "dnr_scale_loss_fwd": (1, 0), "dnr_scale_loss_bwd": (1, 0),
     "dnr_l1_fwd": (1, 0), "dnr_l1_bwd": (1, 0), "dnr_u8_to_f32": (1, 0),
     "dnr_ssim_fwd": (1, 0), "dnr_ssim_bwd": (1, 0), "dnr_adam_step": (1, 0),
+    "dnr_knn_build": (2, 1), "dnr_knn_query": (1, 0), "dnr_density": (1, 0), "dnr_ray_densities": (1, 0),
 }
 LAUNCHES = {"handwritten": 0, "cub": 0}
 
@@ -129,6 +136,19 @@ def load():
     lib.dnr_ssim_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dnr_adam_step.restype = C.c_int
     lib.dnr_adam_step.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p]
+    lib.dnr_knn_workspace_bytes.restype = C.c_int64
+    lib.dnr_knn_workspace_bytes.argtypes = [C.c_int32, C.c_void_p]
+    lib.dnr_knn_build.restype = C.c_int
+    lib.dnr_knn_build.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.dnr_knn_query.restype = C.c_int
+    lib.dnr_knn_query.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
+    lib.dnr_density.restype = C.c_int
+    lib.dnr_density.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]
+    lib.dnr_ray_densities.restype = C.c_int
+    lib.dnr_ray_densities.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dnr_ssim_bwd.restype = C.c_int
     lib.dnr_ssim_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]
@@ -146,7 +166,8 @@ EXPORTS = (
     "dnr_version", "dnr_error_string", "dnr_project_fwd", "dnr_bin_scan_workspace_bytes", "dnr_bin_scan",
     "dnr_bin_sort_workspace_bytes", "dnr_bin_sort", "dnr_depth_order_ptr", "dnr_raster_fwd", "dnr_finalize_fwd", "dnr_normal_from_depth",
     "dnr_raster_bwd", "dnr_project_bwd", "dnr_loss_fwd", "dnr_loss_bwd", "dnr_scale_loss_fwd", "dnr_scale_loss_bwd",
-    "dnr_l1_fwd", "dnr_l1_bwd", "dnr_u8_to_f32", "dnr_ssim_fwd", "dnr_ssim_bwd", "dnr_adam_step",
+    "dnr_l1_fwd", "dnr_l1_bwd", "dnr_u8_to_f32", "dnr_ssim_fwd", "dnr_ssim_bwd", "dnr_adam_step", "dnr_knn_workspace_bytes", "dnr_knn_build", "dnr_knn_query",
+    "dnr_density", "dnr_ray_densities",
 )
 
 

@@ -25,6 +25,8 @@ SOURCES = {
     "misc.cu": [],
     "ssim.cu": [],
     "adam.cu": ["-fmad=false"],
+    "knn.cu": ["-fmad=false"],
+    "density.cu": ["-fmad=false"],
 }
 
 

@@ -36,3 +36,15 @@ def project_pix(p: Tensor, fx: float, fy: float, cx: float, cy: float, c2w: Tens
     pc = (p.to(device) - c2w[..., :3, 3]) @ c2w[..., :3, :3]
     u, v = pc[:, 0] * fx / pc[:, 2] + cx, pc[:, 1] * fy / pc[:, 2] + cy
     return torch.stack([u, v, pc[:, 2]], dim=-1) if return_z_depths else torch.stack([u, v], dim=-1)
+
+
+def get_colored_points_from_depth(depths: Tensor, rgbs: Tensor, c2w: Tensor, fx: float, fy: float, cx: float, cy: float,
+                                  img_size: tuple, mask: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """Coloured world points of a depth + rgb frame (reference :175-210)."""
+    points, _ = get_means3d_backproj(depths=depths.float(), fx=fx, fy=fy, cx=cx, cy=cy, img_size=img_size, c2w=c2w.float(),
+                                     device=depths.device)
+    colors = rgbs.reshape(-1, 3)
+    if mask is not None:
+        mask = torch.as_tensor(mask, device=depths.device)
+        return points[mask], colors[mask]
+    return points, colors

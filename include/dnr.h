@@ -226,6 +226,36 @@ typedef struct DnrAdamSeg {
 } DnrAdamSeg;
 int dnr_adam_step(const DnrAdamSeg* segs /* HOST array */, int32_t n_segs, double beta1, double beta2, void* stream);
 
+/* ---- SuGaR-style queries (EXPERIMENTAL in round 1: opt-in through dn_splatter_b200.sugar) ----
+ * Grid-hash k-NN: replaces sklearn behind dn_splatter/utils/knn.py:29-43 (knn_sk) and nerfstudio's k_nearest_sklearn
+ * (dn_model.py:187).  The host chooses the grid; points outside it are clamped into the border cells (still exact). */
+typedef struct DnrKnnGrid {
+  float lo[3];     /* origin of cell (0,0,0) */
+  float cell;      /* cell edge */
+  float inv_cell;  /* 1 / cell */
+  int32_t dims[3]; /* cells per axis; product <= 2^26 */
+} DnrKnnGrid;
+int64_t dnr_knn_workspace_bytes(int32_t n_points, const DnrKnnGrid* grid);
+int dnr_knn_build(const float* points /* [n,3] */, int32_t n_points, const DnrKnnGrid* grid, void* ws, int64_t ws_bytes,
+                  void* stream);
+/* out_idx [n_queries,k] int64 (-1 where fewer than k points exist), out_dist [n_queries,k] Euclidean or NULL.
+ * skip_first != 0 reproduces knn_sk: search k+1 and drop the nearest (the query itself when it is a data point). */
+int dnr_knn_query(int32_t n_points, const DnrKnnGrid* grid, const void* ws, const float* queries /* [m,3] */,
+                  int32_t n_queries, int32_t k, int32_t skip_first, int64_t* out_idx, float* out_dist, void* stream);
+/* Density of the Gaussian set at samples [n,3] given neighbour lists nbr_idx [n / samples_per_row, k] (int64, -1 =
+ * none): get_density (dn_model.py:1077-1135) with clamp_min = 1e-4.  Raw parameters (log-scales, opacity logits,
+ * un-normalised wxyz quats). */
+int dnr_density(const float* samples, int64_t n_samples, const int64_t* nbr_idx, int32_t k, int32_t samples_per_row,
+                const float* means, const float* scales, const float* quats, const float* opacities, int32_t n_gauss,
+                float clamp_min, float* out, void* stream);
+/* The ray sampling of compute_level_surface_points (dn_model.py:1264-1345): for each point p (a back-projected
+ * pixel) 21 samples p + t_j d, t_j = linspace(-range, range, 21) * std(first neighbour), d = normalize(p - cam).
+ * out_dens / out_t [n_points,21], out_dirs [n_points,3].  cam_pos_host: 3 floats on the HOST. */
+int dnr_ray_densities(const float* points, int64_t n_points, const int64_t* nbr_idx, int32_t k, const float* cam_pos_host,
+                      const float* means, const float* scales, const float* quats, const float* opacities,
+                      int32_t n_gauss, int32_t n_range, float range_size, float* out_dens, float* out_t, float* out_dirs,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

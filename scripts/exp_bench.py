@@ -128,7 +128,29 @@ def bench_project_bwd():
     emit({"row": "project_bwd", "default_ms": res[False], "compact_ms": res[True], "grad_rel_err": rel})
 
 
-for name, fn in (("ssim", bench_ssim), ("adam", bench_adam), ("project_bwd", bench_project_bwd)):
+def bench_knn():
+    import time
+
+    from dn_splatter_b200.sugar import KnnIndex
+    from oracle import sugar_ref as S  # sklearn, the reference's backend: timed on the host as the baseline
+
+    n, m = args.n, 200_000
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, 3, generator=g) * torch.tensor([3.0, 3.0, 0.5])
+    y = x[torch.randint(0, n, (m,), generator=g)] + 0.01 * torch.randn(m, 3, generator=g)
+    xc, yc = x.cuda(), y.cuda()
+    t_build = timed(lambda: KnnIndex(xc), 5)
+    index = KnnIndex(xc)
+    t_query = timed(lambda: index.query(yc, 16), 5)
+    t0 = time.time()
+    want = S.knn_sk(x, y[:20_000], 16)
+    t_sk = (time.time() - t0) * 1e3 * (m / 20_000)
+    got = index.query(yc[:20_000], 16).cpu()
+    emit({"row": "knn", "n_points": n, "n_queries": m, "build_ms": t_build, "query_ms": t_query,
+          "sklearn_ms_extrapolated": t_sk, "index_agreement": float((got == want).float().mean())})
+
+
+for name, fn in (("ssim", bench_ssim), ("adam", bench_adam), ("project_bwd", bench_project_bwd), ("knn", bench_knn)):
     if args.only and name not in args.only.split(","):
         continue
     try:

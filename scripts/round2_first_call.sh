@@ -4,7 +4,7 @@
 # Every stage runs under its own timeout and writes into gpurun_out/; nothing here changes the default path.
 mkdir -p gpurun_out
 export DNR_TEST_EXPERIMENTAL=1
-timeout 300 python -m pytest tests -q -m gpu -k "experimental or fused_ssim or fused_adam" > gpurun_out/r2_experimental_tests.log 2>&1
+timeout 300 python -m pytest tests -q -m gpu -k "experimental or fused_ssim or fused_adam or sugar" > gpurun_out/r2_experimental_tests.log 2>&1
 echo "experimental tests rc=$?"
 timeout 300 python scripts/exp_bench.py > gpurun_out/r2_exp_bench.jsonl 2> gpurun_out/r2_exp_bench.err
 echo "exp_bench rc=$?"; cat gpurun_out/r2_exp_bench.jsonl

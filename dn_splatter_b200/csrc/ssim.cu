@@ -21,7 +21,11 @@ constexpr int SS_R = 5;            // window radius
 constexpr int SS_T = 16;           // output tile
 constexpr int SS_H = SS_T + 2 * SS_R;  // halo tile edge (26)
 
-__constant__ float c_win[11];  // normalised 1-D Gaussian, sigma 1.5 (filled by ensure_window)
+// normalised 1-D Gaussian, sigma 1.5: exp(-d^2 / 4.5) / sum, evaluated in fp32 exactly as torchmetrics' _gaussian does
+// (statically initialised: no host state, valid on every device of the process, nothing to do under graph capture)
+__constant__ float c_win[11] = {1.028380357e-03f, 7.598758209e-03f, 3.600077331e-02f, 1.093606874e-01f, 2.130055279e-01f,
+                                2.660117149e-01f, 2.130055279e-01f, 1.093606874e-01f, 3.600077331e-02f, 7.598758209e-03f,
+                                1.028380357e-03f};
 
 __device__ __forceinline__ float ld_img(const float* __restrict__ img, int H, int W, int C, int i, int j, int c) {
   return (i >= 0 && i < H && j >= 0 && j < W) ? img[((size_t)i * W + j) * C + c] : 0.f;
@@ -123,18 +127,6 @@ __global__ void __launch_bounds__(SS_T* SS_T) ssim_bwd_kernel(const float* __res
   }
 }
 
-int ensure_window() {
-  static bool done = false;
-  if (done) return 0;
-  float w[11], s = 0.f;
-  for (int k = 0; k < 11; ++k) { const float d = (float)(k - 5); w[k] = expf(-(d * d) / (2.f * 1.5f * 1.5f)); s += w[k]; }
-  for (int k = 0; k < 11; ++k) w[k] /= s;
-  cudaError_t e = cudaMemcpyToSymbol(c_win, w, sizeof(w));
-  if (e != cudaSuccess) return (int)e;
-  done = true;
-  return 0;
-}
-
 }  // namespace
 
 // pred / gt: [H,W,C] fp32.  dmaps: [3,H,W,C] scratch kept for the backward.  *mean_out (zeroed by the call) receives the
@@ -143,8 +135,6 @@ extern "C" int dnr_ssim_fwd(const float* pred, const float* gt, int32_t H, int32
                             void* stream) {
   if (!pred || !gt || !dmaps || !sum_out) return DNR_E_NULL;
   if (H <= 2 * SS_R || W <= 2 * SS_R || C <= 0) return DNR_E_SIZE;
-  const int rc = ensure_window();
-  if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   DNR_CUDA(cudaMemsetAsync(sum_out, 0, sizeof(float), s));
   const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, C), block(SS_T, SS_T);
@@ -158,8 +148,6 @@ extern "C" int dnr_ssim_bwd(const float* pred, const float* gt, int32_t H, int32
                             const float* v_mean, float* v_pred, void* stream) {
   if (!pred || !gt || !dmaps || !v_pred) return DNR_E_NULL;
   if (H <= 2 * SS_R || W <= 2 * SS_R || C <= 0) return DNR_E_SIZE;
-  const int rc = ensure_window();
-  if (rc) return rc;
   const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, C), block(SS_T, SS_T);
   ssim_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(pred, gt, H, W, C, dmaps, v_mean, v_pred);
   DNR_CHECK_LAUNCH();

@@ -393,11 +393,14 @@ class DNSplatterModel(torch.nn.Module):
         # Per-camera constants are cached on the camera object as HOST tensors and handed to the kernels by value:
         # the step issues no H2D copy and no device op for the camera (camera optimisation is off on this path).
         cache = camera.__dict__.setdefault("_dnr_cache", {})
-        if scale_fac not in cache:
-            c2w_host = camera.camera_to_worlds.reshape(-1, 3, 4)[0].detach().float().cpu()
-            cache[scale_fac] = (camera.get_intrinsics_matrices()[0].float().cpu(), int(camera.width.flatten()[0]),
-                                int(camera.height.flatten()[0]), c2w_host, get_viewmat(c2w_host))
-        K, W, H, c2w_fixed, viewmat = cache[scale_fac]
+        pose = camera.camera_to_worlds
+        key = (scale_fac, pose.data_ptr(), pose._version)  # an in-place pose update invalidates the entry
+        if key not in cache:
+            cache.clear()
+            c2w_host = pose.reshape(-1, 3, 4)[0].detach().float().cpu()
+            cache[key] = (camera.get_intrinsics_matrices()[0].float().cpu(), int(camera.width.flatten()[0]),
+                          int(camera.height.flatten()[0]), c2w_host, get_viewmat(c2w_host))
+        K, W, H, c2w_fixed, viewmat = cache[key]
         fixed_capacity = 0
         gc = self.__dict__.get("_graph_cam")
         if gc is not None:  # CUDA-graph mode: camera in static device buffers (refreshed before each replay), fixed capacity

@@ -79,3 +79,13 @@ def test_ags_mesh_strategy_path_runs_and_needs_confidence():
         assert torch.isfinite(ld["main_loss"])
         with pytest.raises((NameError, UnboundLocalError, TypeError)):  # quirk B15: confidence is required
             m.get_loss_dict(m.get_outputs(cam), dict(batch))
+
+
+def test_camera_cache_follows_in_place_pose_updates():
+    with cpu_proxy():
+        m, cam, batch, _ = _setup()
+        a = m.get_outputs(cam)["rgb"].detach().clone()
+        assert torch.equal(m.get_outputs(cam)["rgb"], a)  # cached camera constants: same view
+        cam.camera_to_worlds[0, 0, 3] += 0.3  # move the camera in place
+        b = m.get_outputs(cam)["rgb"].detach()
+        assert float((a - b).abs().max()) > 1e-3

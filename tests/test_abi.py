@@ -89,6 +89,29 @@ def test_argument_errors_are_negative_codes(lib):
     assert lib.dnr_bin_sort_workspace_bytes(1000, 5000, 64) > 5000 * 8
 
 
+def test_argument_errors_of_the_8f_entry_points(lib):
+    """SSIM / Adam / k-NN / density validate their arguments before touching the GPU."""
+    one = C.c_void_p(16)  # a non-NULL dummy: the size checks come first, nothing is dereferenced
+    assert lib.dnr_ssim_fwd(None, one, 32, 32, 3, one, one, None) == -1
+    assert lib.dnr_ssim_fwd(one, one, 10, 32, 3, one, one, None) == -2  # an 11x11 window needs H, W > 10
+    assert lib.dnr_ssim_bwd(one, one, 32, 32, 3, None, None, one, None) == -1
+    assert lib.dnr_adam_step(None, 1, 0.9, 0.999, None) == -1
+    seg = (L.DnrAdamSeg * 1)()
+    assert lib.dnr_adam_step(C.cast(seg, C.c_void_p), 0, 0.9, 0.999, None) == -2
+    assert lib.dnr_adam_step(C.cast(seg, C.c_void_p), 17, 0.9, 0.999, None) == -2  # DNR_ADAM_MAX_SEGS = 16
+    assert lib.dnr_adam_step(C.cast(seg, C.c_void_p), 1, 0.9, 0.999, None) == -1  # NULL tensors in the segment
+    g = L.DnrKnnGrid()
+    assert lib.dnr_knn_workspace_bytes(100, C.byref(g)) == -1  # zero dims
+    g.cell, g.inv_cell = 0.5, 2.0
+    g.dims[0], g.dims[1], g.dims[2] = 8, 8, 8
+    assert lib.dnr_knn_workspace_bytes(100, C.byref(g)) >= 100 * (4 + 4 + 4 + 4 + 16) + 2 * 512 * 4
+    assert lib.dnr_knn_build(None, 100, C.byref(g), one, 1 << 20, None) == -1
+    assert lib.dnr_knn_build(one, 100, C.byref(g), one, 8, None) == -5  # workspace too small
+    assert lib.dnr_knn_query(100, C.byref(g), one, one, 5, 40, 1, one, None, None) == -3  # k + 1 > 33
+    assert lib.dnr_density(one, 0, one, 16, 1, one, one, one, one, 10, 0.0, one, None) == -2
+    assert lib.dnr_ray_densities(one, 5, one, 16, one, one, one, one, one, 10, 20, 3.0, one, one, one, None) == -3  # 21 samples only
+
+
 def test_product_path_fails_loudly_without_cuda():
     import torch
 

@@ -144,6 +144,60 @@ def get_sdf_weight(model, closest_gaussians_idx: Tensor) -> Tensor:
     return torch.exp(model.gauss_params["scales"]).min(dim=-1)[0][closest_gaussians_idx].mean(dim=1)
 
 
+def sample_points_in_gaussians(model, num_samples: int, vis_indices: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """dn_model.py:954-1004: pick Gaussians with probability given by the CUMULATIVE volume fractions (the reference
+    hands the cumulative sums, not the volumes, to torch.multinomial — kept), then draw one point from each."""
+    gp = model.gauss_params
+    ext = torch.exp(gp["scales"] if vis_indices is None else gp["scales"][vis_indices])
+    vol = (ext[..., 0] * ext[..., 1] * ext[..., 2]).abs()
+    weights = vol.cumsum(dim=-1) / vol.sum(dim=-1, keepdim=True)
+    picked = torch.multinomial(weights, num_samples=num_samples, replacement=True)
+    if vis_indices is not None:
+        picked = vis_indices[picked]
+    noise = torch.randn(size=(len(picked), 3), device=gp["means"].device, dtype=torch.float)
+    local = torch.exp(gp["scales"][picked]) * noise
+    offsets = torch.bmm(_quat_to_rotmat(gp["quats"][picked]), local[..., None]).squeeze()
+    return gp["means"][picked] + offsets, picked
+
+
+def get_ideal_sdf(model, sdf_samples: Tensor, depth: Tensor, camera, mask: Optional[Tensor] = None,
+                  min_depth: float = 0.01) -> Tuple[Tensor, Tensor]:
+    """dn_model.py:1006-1058: rendered depth at the pixel a sample projects to, minus the sample's own z-depth.
+    Reference quirks kept: fx is used for BOTH focal lengths, and pixel row / column 0 count as invalid (strict > 0)."""
+    from .utils.camera_utils import project_pix
+
+    c2w = camera.camera_to_worlds.squeeze(0)
+    c2w = c2w @ torch.diag(torch.tensor([1, -1, -1, 1], device=c2w.device, dtype=c2w.dtype))
+    fx = float(camera.fx.flatten()[0])
+    proj = project_pix(sdf_samples, fx=fx, fy=fx, cx=float(camera.cx.flatten()[0]), cy=float(camera.cy.flatten()[0]),
+                       c2w=c2w, device=sdf_samples.device, return_z_depths=True)
+    uv = torch.floor(proj[:, :2]).long()
+    W, H = int(camera.width.flatten()[0]), int(camera.height.flatten()[0])
+    in_image = (uv[:, 0] > 0) & (uv[:, 0] < W) & (uv[:, 1] > 0) & (uv[:, 1] < H)
+    valid = in_image
+    if mask is not None:
+        valid = in_image.detach().clone()
+        valid[in_image] = mask[uv[in_image, 1], uv[in_image, 0]][..., 0]
+    return depth[uv[valid, 1], uv[valid, 0], 0] - proj[valid][..., -1], valid
+
+
+@torch.no_grad()
+def get_sdf_loss_weight(model, valid_indices: Tensor, mode: str = "std") -> Optional[Tensor]:
+    """dn_model.py:1167-1204: per-Gaussian weight of the sdf loss — product of the two largest extents ("area") or the
+    standard deviation along the direction to the camera of the last rendered view ("std")."""
+    gp = model.gauss_params
+    if mode == "area":
+        ext = torch.exp(gp["scales"][valid_indices]).clone().detach()
+        return torch.prod(torch.gather(ext, dim=-1, index=torch.topk(ext, k=2, dim=-1)[1]), dim=-1)
+    if mode == "std":
+        cam_pos = model.camera.camera_to_worlds.detach()[..., :3, 3]
+        view = cam_pos - gp["means"][valid_indices].detach()
+        view = view / view.norm(dim=-1, keepdim=True)
+        Rt = _quat_to_rotmat(gp["quats"][valid_indices]).transpose(-1, -2)  # R(q^-1)
+        return (torch.exp(gp["scales"][valid_indices]) * torch.bmm(Rt, view[..., None])[..., 0]).norm(dim=-1)
+    return None
+
+
 def _quat_to_rotmat(q: Tensor) -> Tensor:
     w, x, y, z = torch.unbind(torch.nn.functional.normalize(q, dim=-1), dim=-1)
     return torch.stack([

@@ -81,6 +81,23 @@ def main():
         z["q_sdf"] = M.DNSplatterModel.get_sdf(m, samples, closest_gaussians=idx).numpy()
         z["q_density_grad"] = M.DNSplatterModel.get_density_grad(m, samples, closest_gaussians=idx).numpy()
         z["q_sdf_weight"] = M.DNSplatterModel.get_sdf_weight(m, idx).numpy()
+        # sampling / ideal sdf / loss weights (dn_model.py:954-1058, 1167-1204); m.camera was set by get_outputs
+        m.training = False
+        vis = torch.where(m.radii > 0)[0][::2].clone()
+        for tag, vi in (("all", None), ("vis", vis)):
+            torch.manual_seed(99)
+            pts, ids = M.DNSplatterModel.sample_points_in_gaussians(m, 200, vis_indices=vi)
+            z[f"samp_{tag}_points"], z[f"samp_{tag}_ids"] = pts.numpy(), ids.numpy()
+        z["samp_vis_indices"] = vis.numpy()
+        depth = M.DNSplatterModel.get_outputs(m, camera)["depth"]
+        z["ideal_depth_map"] = depth.numpy()
+        mask = (torch.rand(H, W, 1, generator=g) > 0.3)
+        for tag, mk in (("nomask", None), ("mask", mask)):
+            sdf, valid = M.DNSplatterModel.get_ideal_sdf(m, torch.from_numpy(z["samp_all_points"]), depth, camera, mask=mk)
+            z[f"ideal_{tag}_sdf"], z[f"ideal_{tag}_valid"] = sdf.numpy(), valid.numpy()
+        z["ideal_mask"] = mask.numpy()
+        for mode in ("area", "std"):
+            z[f"lossw_{mode}"] = M.DNSplatterModel.get_sdf_loss_weight(m, torch.from_numpy(z["samp_all_ids"]), mode=mode).numpy()
     np.savez_compressed(os.path.join(OUT, "dn_sugar_a.npz"), **z)
     print("density range", float(z["q_density"].min()), float(z["q_density"].max()), " >=1:", int((z["q_density"] >= 0.99999).sum()))
 

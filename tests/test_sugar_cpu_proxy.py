@@ -95,3 +95,28 @@ def test_no_cpu_path():
 
     with pytest.raises(Exception, match="no CPU path"):
         SG.knn_gpu(torch.zeros(4, 3), torch.zeros(2, 3), 2)
+
+
+def test_sampling_ideal_sdf_and_loss_weights_match_reference(gold):
+    """sample_points_in_gaussians / get_ideal_sdf / get_sdf_loss_weight are device-agnostic torch: run as they are."""
+    import dn_splatter_b200.sugar as SG
+
+    with cpu_proxy():
+        m, cam = _model(gold)
+        out = m.get_outputs(cam)  # sets m.camera (used by the "std" weights) and m.radii
+        vis = torch.where(m.radii > 0)[0][::2]
+        assert torch.equal(vis, gold["samp_vis_indices"])
+        for tag, vi in (("all", None), ("vis", vis)):
+            torch.manual_seed(99)
+            pts, ids = SG.sample_points_in_gaussians(m, 200, vis_indices=vi)
+            assert torch.equal(ids, gold[f"samp_{tag}_ids"])
+            torch.testing.assert_close(pts.detach(), gold[f"samp_{tag}_points"], rtol=1e-5, atol=1e-6)
+        depth = gold["ideal_depth_map"]
+        torch.testing.assert_close(out["depth"], depth, rtol=1e-5, atol=1e-6)
+        for tag, mk in (("nomask", None), ("mask", gold["ideal_mask"])):
+            sdf, valid = SG.get_ideal_sdf(m, gold["samp_all_points"], depth, cam, mask=mk)
+            assert torch.equal(valid, gold[f"ideal_{tag}_valid"])
+            torch.testing.assert_close(sdf, gold[f"ideal_{tag}_sdf"], rtol=1e-5, atol=1e-6)
+        for mode in ("area", "std"):
+            torch.testing.assert_close(SG.get_sdf_loss_weight(m, gold["samp_all_ids"], mode=mode), gold[f"lossw_{mode}"],
+                                       rtol=1e-5, atol=1e-7)

@@ -110,7 +110,7 @@ def _params(model) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
 def _density_call(samples: Tensor, idx: Tensor, model, samples_per_row: int, clamp_min: float) -> Tensor:
     means, scales, quats, opac = _params(model)
     s = samples.detach().float().contiguous()
-    idx = idx.contiguous()
+    idx = idx.long().contiguous()
     out = torch.empty(s.shape[0], dtype=torch.float32, device=s.device)
     if s.shape[0] > 0:
         L.check(L.load().dnr_density(s.data_ptr(), s.shape[0], idx.data_ptr(), idx.shape[1], samples_per_row, means.data_ptr(),
@@ -234,13 +234,14 @@ def ray_densities(model, points: Tensor, idx: Tensor, cam_pos: Tensor, n_range: 
     """Densities at the n_range samples of every pixel ray: (densities [P,n], offsets t [P,n], unit directions [P,3])."""
     means, scales, quats, opac = _params(model)
     p = points.detach().float().contiguous()
+    idx = idx.long().contiguous()
     P = p.shape[0]
     dens = torch.empty((P, n_range), dtype=torch.float32, device=p.device)
     t = torch.empty((P, n_range), dtype=torch.float32, device=p.device)
     dirs = torch.empty((P, 3), dtype=torch.float32, device=p.device)
     if P > 0:
         cam = (C.c_float * 3)(*[float(v) for v in cam_pos.detach().cpu().reshape(3).tolist()])
-        L.check(L.load().dnr_ray_densities(p.data_ptr(), P, idx.contiguous().data_ptr(), idx.shape[1], cam, means.data_ptr(),
+        L.check(L.load().dnr_ray_densities(p.data_ptr(), P, idx.data_ptr(), idx.shape[1], cam, means.data_ptr(),
                                            scales.data_ptr(), quats.data_ptr(), opac.data_ptr(), means.shape[0], n_range,
                                            float(range_size), dens.data_ptr(), t.data_ptr(), dirs.data_ptr(), _stream()),
                 "dnr_ray_densities")

@@ -379,12 +379,6 @@ class DNSplatterModel(torch.nn.Module):
             raise NotImplementedError("crop boxes are viewer-only and outside the hot path")
         if cfg.rasterize_mode not in ("antialiased", "classic"):
             raise ValueError("Unknown rasterize_mode: %s", cfg.rasterize_mode)
-        if cfg.rasterize_mode == "antialiased" and cfg.predict_normals and not self.__dict__.get("_warned_aa"):
-            import warnings
-
-            warnings.warn("rasterize_mode='antialiased' with predict_normals: the normal image is composited with the "
-                          "compensated opacity (the reference's legacy pass uses the un-compensated one); see DESIGN.md §2")
-            self.__dict__["_warned_aa"] = True
         if cfg.sh_degree <= 0:
             raise NotImplementedError("sh_degree == 0 (sigmoid colours) is broken upstream (SURVEY A1.4); not mirrored")
         scale_fac = self._get_downscale_factor()
@@ -410,14 +404,18 @@ class DNSplatterModel(torch.nn.Module):
         sh_degree_to_use = min(self.step // cfg.sh_degree_interval, cfg.sh_degree)
         background = self._get_background_color()
 
-        out = dn_rasterize(
-            self.means, self.quats, self.scales, self.opacities, self.features_dc, self.features_rest, viewmat, K, W, H,
-            sh_degree=sh_degree_to_use, near_plane=0.01, far_plane=1e10, antialiased=cfg.rasterize_mode == "antialiased",
-            background=background, render_normals=cfg.predict_normals,
-            c2w=c2w_fixed,
-            grad_sink=self._bucket.sink() if (self._bucket is not None and torch.is_grad_enabled()) else None,
-            exact_lists=cfg.exact_isect_lists, sync_free=cfg.sync_free, fixed_capacity=fixed_capacity,
-        )
+        # rasterize_mode="antialiased" with normals: the reference's colour pass uses opacity x compensation, its normal
+        # pass (legacy rasterize_gaussians, :564-575) the plain opacity.  One fused pass cannot carry two alpha streams,
+        # so this (non-default) mode renders twice, as the reference does: colour / depth antialiased, normals classic.
+        dual = cfg.rasterize_mode == "antialiased" and cfg.predict_normals
+        common = dict(sh_degree=sh_degree_to_use, near_plane=0.01, far_plane=1e10, background=background, c2w=c2w_fixed,
+                      exact_lists=cfg.exact_isect_lists, sync_free=cfg.sync_free, fixed_capacity=fixed_capacity)
+        params = (self.means, self.quats, self.scales, self.opacities, self.features_dc, self.features_rest, viewmat, K, W, H)
+        sink = self._bucket.sink() if (self._bucket is not None and torch.is_grad_enabled()) else None
+        out = dn_rasterize(*params, antialiased=cfg.rasterize_mode == "antialiased",
+                           render_normals=cfg.predict_normals and not dual, grad_sink=sink, **common)
+        out_n = dn_rasterize(*params, antialiased=False, render_normals=True, surface_normal=False, grad_sink=sink,
+                             **common) if dual else out
         self.raster_out = out
         self.xys = out.means2d[None]  # [1,N,2]; .grad / .absgrad live on out.means2d after backward
         self.xys_flat = out.means2d
@@ -426,8 +424,8 @@ class DNSplatterModel(torch.nn.Module):
         self.conics = out.conics[None]
         self.num_tiles_hit = out.tiles_per_gauss[None]
         if cfg.predict_normals:
-            self.gauss_params["normals"].data = out.normals_world  # reference :558 (same Parameter object)
-            normals_im = out.normal
+            self.gauss_params["normals"].data = out_n.normals_world  # reference :558 (same Parameter object)
+            normals_im = out_n.normal
         else:
             normals_im = torch.full((1, H, W, 3), 0.0)  # quirk B13: CPU zeros
         if getattr(camera, "metadata", None) is not None and "cam_idx" in camera.metadata:

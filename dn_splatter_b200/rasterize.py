@@ -281,7 +281,13 @@ class _DnRasterize(torch.autograd.Function):
             L.check(_timed("bin_scan", lib.dnr_bin_scan, C.byref(a), st, C.byref(total)), "dnr_bin_scan")
             n_isects = int(total.value)
             if s.sync_free:
-                _CAPACITY.setdefault(cap_key, _CapacityTracker()).seed(n_isects)
+                if cap_key not in _CAPACITY:
+                    # the Gaussian count changed (densification): drop the trackers of the old counts for this
+                    # device / resolution instead of keeping one pinned buffer per count ever seen
+                    for stale in [k for k in _CAPACITY if k[0] == cap_key[0] and k[2:] == cap_key[2:] and k[1] != n]:
+                        del _CAPACITY[stale]
+                    _CAPACITY[cap_key] = _CapacityTracker()
+                _CAPACITY[cap_key].seed(n_isects)
         a.n_isects = n_isects
         ws_sort = torch.empty(lib.dnr_bin_sort_workspace_bytes(n, n_isects, n_tiles), dtype=torch.uint8, device=dev)
         flatten_ids = torch.empty(max(n_isects, 1), **i32)

@@ -54,6 +54,20 @@ class DensifyState:
         self.xys_grad_norm = self.vis_counts = self.max_2Dsize = None
 
     @torch.no_grad()
+    def all_reduce_(self, group=None) -> None:
+        """Multi-GPU: every rank saw different views; before a refinement the statistics become those of ALL views
+        (sum of the gradient norms and visibility counts, max of the screen sizes) so that every rank takes the same
+        split / dup / cull decisions.  vis_counts starts at one on each rank: the extra ones are removed again."""
+        import torch.distributed as dist
+
+        from .parallel import all_reduce_densification_stats
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1 or self.vis_counts is None:
+            return
+        all_reduce_densification_stats(self.xys_grad_norm, self.vis_counts, self.max_2Dsize, group)
+        self.vis_counts -= float(dist.get_world_size(group) - 1)
+
+    @torch.no_grad()
     def after_train(self, absgrad: Tensor, radii: Tensor, last_size) -> None:
         """absgrad [N,2] (means2d.absgrad of the view just trained), radii [N] int32, last_size (H, W).  Mask-free
         formulation (no boolean indexing, hence no sync): invisible Gaussians add zero."""

@@ -57,6 +57,9 @@ class Trainer:
         m.after_train(step)
         info: Optional[Dict[str, int]] = None
         if step > 0 and step % m.config.refine_every == 0:
+            st = m.__dict__.get("_densify_state")
+            if self.world_size > 1 and st is not None:
+                st.all_reduce_()  # identical statistics -> identical decisions (and identical split samples: same seed)
             info = m.refinement_after(self.optimizers, step, generator=self.generator)
         self.step += 1
         return {"loss": loss.detach(), "refine": info}

@@ -67,3 +67,50 @@ def test_two_rank_gradient_equals_single_rank():
     for k in GRAD_PARAMS:
         torch.testing.assert_close(got[k], want[k], rtol=1e-6, atol=1e-6)
     assert sorted(shard_views(5, 0, 2) + shard_views(5, 1, 2)) == list(range(5))
+
+
+def _stats_worker(rank, world, port, ret):
+    from dn_splatter_b200.densify import DensifyState
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    st = DensifyState()
+    for v in shard_views(6, rank, world):
+        absgrad, radii = _fake_view_stats(v)
+        st.after_train(absgrad, radii, (48, 64))
+    st.all_reduce_()
+    if rank == 1:
+        ret.put((st.xys_grad_norm.clone(), st.vis_counts.clone(), st.max_2Dsize.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _fake_view_stats(view):
+    g = torch.Generator().manual_seed(100 + view)
+    radii = (torch.rand(40, generator=g) * 6).int() * (torch.rand(40, generator=g) > 0.3).int()
+    return torch.randn(40, 2, generator=g), radii
+
+
+def test_two_rank_densification_statistics_equal_single_rank():
+    from dn_splatter_b200.densify import DensifyState
+
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_stats_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    st = DensifyState()
+    for v in range(6):
+        st.after_train(*_fake_view_stats(v), (48, 64))
+    torch.testing.assert_close(got[0], st.xys_grad_norm, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(got[1], st.vis_counts)
+    torch.testing.assert_close(got[2], st.max_2Dsize)

@@ -150,7 +150,39 @@ def bench_knn():
           "sklearn_ms_extrapolated": t_sk, "index_agreement": float((got == want).float().mean())})
 
 
-for name, fn in (("ssim", bench_ssim), ("adam", bench_adam), ("project_bwd", bench_project_bwd), ("knn", bench_knn)):
+def bench_render_service():
+    """forward-only render-all-views loop (what gs-mesh / ns-eval do), maps kept on the device or copied
+    to pinned host buffers."""
+    import time
+
+    from dn_splatter_b200.cameras import Cameras
+    from dn_splatter_b200.dn_model import DNSplatterModelConfig
+    from dn_splatter_b200.render_service import ViewRenderer
+    from dn_splatter_b200.synthetic import make_scene, ring_cameras
+
+    W, H, n_views = 1920, 1080, 48
+    m = DNSplatterModelConfig(random_init=True, num_random=16, background_color="black", sync_free=True).setup(device="cuda")
+    m.load_gaussians(make_scene(args.n, seed=0))
+    m.step = 30000
+    cams = [Cameras(c["c2w"][None], c["fx"], c["fy"], c["cx"], c["cy"], W, H) for c in ring_cameras(n_views, W, H)]
+    row = {"row": "render_service", "n_gauss": args.n, "views": n_views, "resolution": f"{W}x{H}"}
+    for to_host in (False, True):
+        r = ViewRenderer(m, to_host=to_host)
+        for _ in r.render(cams[:8]):  # warm-up (also seeds the sync-free capacity)
+            pass
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in r.render(cams):
+            pass
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_views
+        row["ms_per_view_host" if to_host else "ms_per_view_device"] = dt * 1e3
+        row["mpix_s_host" if to_host else "mpix_s_device"] = W * H / 1e6 / dt
+    emit(row)
+
+
+for name, fn in (("ssim", bench_ssim), ("adam", bench_adam), ("project_bwd", bench_project_bwd), ("knn", bench_knn),
+                 ("render_service", bench_render_service)):
     if args.only and name not in args.only.split(","):
         continue
     try:

@@ -12,3 +12,5 @@ DNR_RUN_TRAINING_TEST=1 timeout 400 python -m pytest tests/test_gpu_training.py 
 echo "training test rc=$?"; tail -3 gpurun_out/r2_training_test.log
 timeout 400 python scripts/bwd_microbench.py --reps 6 > gpurun_out/r2_bwd_microbench.jsonl 2> gpurun_out/r2_bwd_microbench.err
 echo "bwd_microbench rc=$?"; tail -3 gpurun_out/r2_bwd_microbench.jsonl
+DNR_RUN_SCALE_TEST=1 timeout 300 python -m pytest tests/test_gpu_scale.py -q -m gpu > gpurun_out/r2_scale_test.log 2>&1
+echo "scale test rc=$?"; tail -3 gpurun_out/r2_scale_test.log

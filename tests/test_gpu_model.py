@@ -223,7 +223,6 @@ def _graph_step_body():
 
 
 @needs_cuda
-@pytest.mark.skipif(__import__("os").environ.get("DNR_TEST_EXPERIMENTAL") != "1", reason="experimental kernels: opt-in")
 @pytest.mark.parametrize("hw", [(64, 80), (37, 53), (128, 160), (11, 200)])
 def test_fused_ssim_matches_torch(hw):
     """csrc/ssim.cu (value + gradient) against dn_model.ssim() — the torchmetrics restatement the default path uses."""
@@ -247,7 +246,6 @@ def test_fused_ssim_matches_torch(hw):
 
 
 @needs_cuda
-@pytest.mark.skipif(__import__("os").environ.get("DNR_TEST_EXPERIMENTAL") != "1", reason="experimental kernels: opt-in")
 def test_fused_adam_matches_torch_adam():
     """optim.FusedAdam (one dnr_adam_step launch) against one torch.optim.Adam per group over 20 steps, odd sizes
     (scalar tail, unaligned views) included."""

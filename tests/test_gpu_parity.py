@@ -187,7 +187,6 @@ def test_sync_free_capacity_mode_matches_sync_mode():
 
 
 @needs_cuda
-@pytest.mark.skipif(__import__("os").environ.get("DNR_TEST_EXPERIMENTAL") != "1", reason="experimental kernels: opt-in")
 @pytest.mark.parametrize("case", CASES[:2])
 def test_experimental_compact_project_bwd_matches_default(case):
     """DNR_FLAG_COMPACT_BWD (round-2 candidate) must give the default backward's gradients."""

@@ -1,15 +1,13 @@
 """BASELINE.json configs[2] / configs[3] sizes (3M Gaussians @1080p with normals; 6M Gaussians @2560x1440): one
 forward + backward each, checked through size-independent properties (finite outputs, alpha in [0,1], sorted tile
-lists within int32 range, gradients finite and non-zero, precise-hit == exact lists on the images).  Opt-in
-(DNR_RUN_SCALE_TEST=1): ~2 GB of scene + a few GB of intersection buffers, a few seconds on a B200; written after round
-1's GPU budget was spent."""
+lists within int32 range, gradients finite and non-zero, precise-hit == exact lists on the images).  ~2 GB of scene + a few GB of
+intersection buffers, a few seconds on a B200."""
 import os
 
 import pytest
 import torch
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DNR_RUN_SCALE_TEST") != "1", reason="large-scene test: opt-in"),
               pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
 
 

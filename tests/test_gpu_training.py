@@ -4,19 +4,11 @@ without breaking the optimizer state or the flat gradient bucket."""
 import pytest
 import torch
 
-import os
-
 pytestmark = pytest.mark.gpu
 needs_cuda = pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")
-# Round-1 status: the one GPU run of this test densified every few steps with an absurdly low threshold (every Gaussian
-# split each time), which legitimately drives the loss up; tests/test_training_cpu_proxy.py reproduced that on the CPU and
-# validates the corrected schedule below with the oracle substituted for the kernels.  The GPU budget was exhausted
-# before this version could run on a B200, so it stays opt-in until round 2 confirms it.
-opt_in = pytest.mark.skipif(os.environ.get("DNR_RUN_TRAINING_TEST") != "1", reason="opt-in: set DNR_RUN_TRAINING_TEST=1")
 
 
 @needs_cuda
-@opt_in
 def test_training_loop_reduces_loss_and_densifies():
     from dn_splatter_b200.cameras import Cameras
     from dn_splatter_b200.dn_model import DNSplatterModelConfig

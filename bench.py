@@ -5,11 +5,12 @@
     python bench.py --impl reference ...                           # the reference's CPU path (oracle port)
     torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU, per-camera sharding
 
-A step = one pass of the hot path over one batch: every rank renders ONE 1080p view of the 1M-Gaussian
-synthetic scene through the public API (DNSplatterModel.get_outputs -> get_loss_dict -> backward):
-project -> bin/sort -> composite RGB+depth+normal -> depth fill + surface normal -> DNRegularization
-(EdgeAwareLogL1 depth, L1+TV normal, min-scale) + L1 photometric -> raster backward -> projection backward
-(straight into the flat gradient bucket) -> [N>1: one NCCL all-reduce of the bucket].
+A step = one training iteration of the reference on one batch: every rank renders ONE 1080p view of the 1M-Gaussian
+synthetic scene through the public API (DNSplatterModel.get_outputs -> get_loss_dict -> backward -> optimizer step):
+project -> bin/sort (supertile lists) -> composite RGB+depth+normal -> depth fill + surface normal -> photometric loss
+(0.8 L1 + 0.2 (1-SSIM), the reference's default ssim_lambda) + DNRegularization (EdgeAwareLogL1 depth, L1+TV normal,
+min-scale) -> raster backward (loss gradients evaluated in its prologue) -> projection backward (straight into the flat
+gradient bucket) -> [N>1: one NCCL all-reduce of the bucket] -> Adam step of the six parameter groups (one launch).
 `value` is measured with the supervision maps resident in HBM; `e2e` pulls each step's maps from pinned host
 memory (H2D inside the timed region) and reads the loss back (D2H).
 """
@@ -50,8 +51,15 @@ def parse():
     ap.add_argument("--cpu-crop", default="512x288")
     ap.add_argument("--sync", action="store_true", help="read the intersection count back every view (host sync)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph captured step")
-    ap.add_argument("--graph-multi", action="store_true", help="capture the step in a CUDA graph on multi-rank runs too "
-                                                                "(not validated in round 1; the all-reduce stays outside the graph)")
+    ap.add_argument("--no-graph-multi", action="store_true", help="multi-rank runs: launch eagerly instead of replaying the "
+                                                                   "captured step (the all-reduce stays outside the graph)")
+    ap.add_argument("--no-ssim", action="store_true", help="ssim_lambda = 0 (round-1 step: L1 only)")
+    ap.add_argument("--no-optimizer", action="store_true", help="leave the Adam step out of the step (round-1 step)")
+    ap.add_argument("--list-shift", type=int, default=2, help="intersection lists per (16 << s)-pixel supertile")
+    ap.add_argument("--variant", type=int, default=0, help="raster kernel tuning knob (A/B timing)")
+    ap.add_argument("--no-fused-loss-bwd", action="store_true", help="loss gradients as images from separate kernels (A/B)")
+    ap.add_argument("--epochs", type=int, default=5, help="extra, untimed-by-contract measurement: median ms/view over this "
+                                                          "many passes over ALL views (0 = skip)")
     return ap.parse_args()
 
 
@@ -131,8 +139,9 @@ def build_workload(args, device, normals: bool):
 
     cfg = DNSplatterModelConfig(
         random_init=True, num_random=16, use_depth_loss=True, depth_lambda=0.2, depth_loss_type=DepthLossType.EdgeAwareLogL1,
-        predict_normals=normals, use_normal_loss=normals, normal_supervision="mono", ssim_lambda=0.0, background_color="black",
-        sync_free=not args.sync,
+        predict_normals=normals, use_normal_loss=normals, normal_supervision="mono",
+        ssim_lambda=0.0 if args.no_ssim else 0.2, background_color="black", sync_free=not args.sync,
+        list_shift=args.list_shift, fuse_loss_backward=not args.no_fused_loss_bwd,
     )
     model = cfg.setup(device=device)
     model.load_gaussians(make_scene(args.n_gauss, seed=0))
@@ -140,6 +149,7 @@ def build_workload(args, device, normals: bool):
     model.step = 30000  # full SH degree (sh_degree_interval schedule done)
     model.train()
     bucket = model.enable_flat_grads()
+    model.__dict__["_raster_variant"] = args.variant
     cams = [Cameras(c["c2w"][None], c["fx"], c["fy"], c["cx"], c["cy"], c["width"], c["height"],
                     metadata={"cam_idx": i}) for i, c in enumerate(ring_cameras(args.views, args.width, args.height))]
     return model, bucket, cams
@@ -172,7 +182,7 @@ def make_gt_sets(model, cams, args, normals: bool, n_sets: int):
     return sets
 
 
-def run_step(model, bucket, cam, batch, reduce=True):
+def run_step(model, bucket, cam, batch, reduce=True, optimizer=None):
     bucket.zero_()
     outputs = model.get_outputs(cam)
     loss_dict = model.get_loss_dict(outputs, dict(batch))
@@ -180,6 +190,8 @@ def run_step(model, bucket, cam, batch, reduce=True):
     loss.backward()
     if reduce:
         bucket.all_reduce()
+    if optimizer is not None:
+        optimizer.step()
     return loss
 
 
@@ -201,6 +213,12 @@ def cpu_reference_sample(args, normals: bool, crop: str):
     cx, cy = cam["cx"] - (args.width - cw) / 2, cam["cy"] - (args.height - ch) / 2
     g = torch.Generator().manual_seed(1)
     gt_img = torch.rand(ch, cw, 3, generator=g).clamp(min=10 / 255.0)
+    opt = None
+    if not args.no_optimizer:  # the reference's per-group Adam (dn_config.py:29-68), stepped inside the sample like ours
+        from dn_splatter_b200.dn_config import optimizer_groups
+
+        groups = optimizer_groups()
+        opt = [torch.optim.Adam([p], lr=groups[k]["lr"], eps=groups[k]["eps"]) for k, p in params.items() if k in groups]
     t0 = time.perf_counter()
     out = dn_ref.get_outputs(params, cam["c2w"], cam["fx"], cam["fy"], cx, cy, cw, ch, torch.tensor(BACKGROUND),
                              predict_normals=normals)
@@ -208,13 +226,24 @@ def cpu_reference_sample(args, normals: bool, crop: str):
     gt_normal = out["surface_normal"].detach()
     reg = dn_ref.dn_regularization(out["depth"], gt_depth, out["normal"], gt_normal, params["scales"], gt_img,
                                    depth_lambda=0.2, use_normal_loss=normals)
-    loss = (out["rgb"] - gt_img).abs().mean() + reg
+    l1 = (out["rgb"] - gt_img).abs().mean()
+    if args.no_ssim:
+        photo = l1
+    else:  # torchmetrics SSIM restated in torch (the reference's default ssim_lambda = 0.2, dn_model.py:180,624-628)
+        from dn_splatter_b200.dn_model import ssim
+
+        photo = 0.8 * l1 + 0.2 * (1 - ssim(gt_img.permute(2, 0, 1)[None], out["rgb"].permute(2, 0, 1)[None]))
+    loss = photo + reg
     loss.backward()
+    if opt is not None:
+        for o in opt:
+            o.step()
     dt = time.perf_counter() - t0
+    sample = (f"1 view, centred {cw}x{ch} crop of the {args.width}x{args.height} frame, N={args.n_gauss}, fwd+bwd"
+              f"{'' if args.no_ssim else '+SSIM'}{'' if args.no_optimizer else '+Adam(dense, all N)'}, {dt:.1f} s")
     return {"value": cw * ch / 1e6 / dt, "unit": "Mpix/s", "cores": cores, "kind": "port",
-            "sample": f"1 view, centred {cw}x{ch} crop of the {args.width}x{args.height} frame, N={args.n_gauss}, fwd+bwd, "
-                      f"{dt:.1f} s; oracle/ = CPU port of gsplat-1.0.0 + the reference's own loss code (gsplat is CUDA-only "
-                      f"and absent)"}, dt
+            "sample": sample + "; oracle/ = CPU port of gsplat-1.0.0 + the reference's own loss code (gsplat is CUDA-only "
+                               "and absent)"}, dt
 
 
 def reference_arm(args):
@@ -233,22 +262,41 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1e3 * (int(args.cpu_crop.split("x")[0]) * int(args.cpu_crop.split("x")[1]) / 1e6) / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, normals, 1), "cpu_baseline": last,
+        "config": workload_config(args, normals, 1, sample=f"each timed step = ONE view cropped to the centred {args.cpu_crop} window of the "
+                                                              f"{args.width}x{args.height} frame (the full frame takes minutes per view on "
+                                                              f"the host); Mpix/s counts the crop's pixels only"),
+        "cpu_baseline": last,
         "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, normals, world):
-    return {
+def workload_config(args, normals, world, sample=None):
+    ssim = not args.no_ssim
+    opt = not args.no_optimizer
+    cfg = {
         "workload": f"BASELINE configs[1]: {args.n_gauss} Gaussians, {args.views} synthetic ring views {args.width}x{args.height}, "
                     f"{'RGB+depth+normal' if normals else 'RGB+depth'} render fwd+bwd, 1 view per GPU per step",
         "n_gauss": args.n_gauss, "width": args.width, "height": args.height, "views": args.views, "sh_degree": 3,
-        "normals": normals, "losses": "L1 rgb + DNRegularization(EdgeAwareLogL1 depth (1+0.2), L1+TV normal, min-scale); "
-                                      "SSIM and the optimizer step are SURVEY §8f 'next' rows, not in the step",
+        "normals": normals,
+        "losses": ("0.8 L1 + 0.2 (1-SSIM) rgb (the reference's default ssim_lambda)" if ssim else "L1 rgb")
+                  + " + DNRegularization(EdgeAwareLogL1 depth (1+0.2), L1+TV normal, min-scale)",
+        "optimizer": "Adam over the six parameter groups with the reference's learning rates, inside the step" if opt else "not in the step",
         "parallelism": f"per-camera sharding x{world}, one flat all-reduce/step" if world > 1 else "single GPU",
-        "l2_policy": "inputs larger than L2 (236 MB parameters + 26M-intersection lists per view)", "gt_sets": args.gt_sets,
+        "l2_policy": "inputs larger than L2 (236 MB parameters + 236 MB gradients + 472 MB Adam moments per step; a different "
+                     "view and supervision set every step)",
+        "gt_sets": args.gt_sets, "view_order": "step s renders view (37 s) mod views of the rank's shard (the ring is sampled evenly)",
     }
+    if sample is not None:
+        cfg["sample"] = sample
+    return cfg
+
+
+VIEW_STRIDE = 37  # coprime with 200: K consecutive steps sample the camera ring evenly
+
+
+def view_of(step: int, my_views):
+    return my_views[(step * VIEW_STRIDE) % len(my_views)]
 
 
 # ------------------------------------------------------------------------------------------------ main (ours)
@@ -272,8 +320,11 @@ def main():
         dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     normals = not args.no_normals
     import dn_splatter_b200.rasterize as R
+    from dn_splatter_b200.optim import FusedAdam
 
     model, bucket, cams = build_workload(args, device, normals)
+    optimizer = None if args.no_optimizer else FusedAdam.for_model(model)
+    stats_dev = torch.zeros(4, dtype=torch.int64, device=device)
     my_views = list(range(rank, len(cams), world)) or [0]
     host_sets = make_gt_sets(model, cams, args, normals, args.gt_sets)
     dev_sets = [{k: v.to(device) for k, v in b.items()} for b in host_sets]
@@ -300,15 +351,21 @@ def main():
 
     graphed = None
 
+    def finish_step():
+        """What follows the (captured) forward + backward: gradient all-reduce, then the Adam step."""
+        bucket.all_reduce()
+        if optimizer is not None:
+            optimizer.step()
+
     def resident_step(s):
-        cam = cams[my_views[s % len(my_views)]]
+        cam = cams[view_of(s, my_views)]
         if graphed is None:
-            run_step(model, bucket, cam, dev_sets[s % len(dev_sets)])
+            run_step(model, bucket, cam, dev_sets[s % len(dev_sets)], optimizer=optimizer)
         else:  # supervision maps: device-resident set -> the graph's static buffers (D2D), then ONE graph launch
             for k, v in dev_sets[s % len(dev_sets)].items():
                 graphed.batches[0][k].copy_(v, non_blocking=True)
             graphed(cam, 0)
-            bucket.all_reduce()
+            finish_step()
 
     losses = []
     copy_stream = torch.cuda.Stream(device=device)
@@ -341,12 +398,12 @@ def main():
         cur = torch.cuda.current_stream()
         cur.wait_event(ready[slot])
         prefetch(s + 1)
-        cam = cams[my_views[s % len(my_views)]]
+        cam = cams[view_of(s, my_views)]
         if graphed is None:
-            loss = run_step(model, bucket, cam, stage[slot])
+            loss = run_step(model, bucket, cam, stage[slot], optimizer=optimizer)
         else:
             loss = graphed(cam, slot)
-            bucket.all_reduce()
+            finish_step()
         consumed[slot].record(cur)
         ls = s % 64
         loss_host[ls:ls + 1].copy_(loss.detach().reshape(1), non_blocking=True)  # D2H read of the step's result
@@ -373,8 +430,7 @@ def main():
     for s in range(max(3, args.warmup)):
         resident_step(s)
     launches_per_step, graph_error = None, None
-    # multi-rank runs launch eagerly: graph capture next to NCCL's watchdog thread is not validated yet
-    if not args.no_graph and (world == 1 or args.graph_multi):
+    if not args.no_graph and (world == 1 or not args.no_graph_multi):
         from dn_splatter_b200 import _lib as _L0
         from dn_splatter_b200.graph_step import GraphedTrainStep
 
@@ -398,8 +454,8 @@ def main():
     launches0 = dict(_L.LAUNCHES)
     ms = timed(args.steps, resident_step)
     launches = {k: _L.LAUNCHES[k] - launches0[k] for k in launches0}
-    if launches_per_step is not None:  # graph replays re-issue the launches recorded at capture
-        launches = {k: v * args.steps for k, v in launches_per_step.items()}
+    if launches_per_step is not None:  # graph replays re-issue the launches recorded at capture (+ the eager Adam step)
+        launches = {k: v * args.steps + launches[k] for k, v in launches_per_step.items()}
     clocks = sampler.stop() if rank == 0 else None
     pix = args.width * args.height
     value = world * args.steps * pix / 1e6 / (ms / 1e3)
@@ -419,32 +475,42 @@ def main():
         e2e = {"value": world * args.steps * pix / 1e6 / (ms_e / 1e3), "unit": "Mpix/s", "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": 4, "ms_per_step": ms_e / args.steps}
 
+    # median over >= 5 passes over the whole view set (the contract's K timed steps above stay the headline)
+    epochs = None
+    if args.epochs > 0:
+        per_epoch = []
+        n_v = len(my_views)
+        for ep in range(args.epochs):
+            per_epoch.append(timed(n_v, lambda s, ep=ep: resident_step(ep * n_v + s)) / n_v)
+        per_epoch.sort()
+        med = per_epoch[len(per_epoch) // 2]
+        epochs = {"epochs": args.epochs, "views_per_epoch_per_rank": n_v, "median_ms_per_step": med,
+                  "min_ms_per_step": per_epoch[0], "max_ms_per_step": per_epoch[-1], "median_value": world * pix / 1e6 / (med / 1e3),
+                  "unit": "Mpix/s"}
+    if graphed is not None:
+        graphed.check_capacity(wait=True)  # raises if any replayed view was truncated
+
     # per-stage device times (CUDA events on the launching stream) for the roofline of the dominant kernel
     stages, roof = {}, None
-    graph_info = ({"capacity": graphed.capacity, "slots": len(graphed.graphs)} if graphed is not None
+    graph_info = ({"capacity": graphed.capacity, "slots": len(graphed.graphs), "max_count": graphed.max_count} if graphed is not None
                   else ({"error": graph_error, "fallback": "eager launches"} if graph_error else None))
     graphed = None  # the instrumented pass below runs eagerly
     if rank == 0:
         R.STAGE_EVENTS = []
+        model.__dict__["_raster_stats"] = stats_dev
         n_prof = min(args.steps, 10)
         for s in range(n_prof):  # rank 0 only: no collective in here
-            run_step(model, bucket, cams[my_views[s % len(my_views)]], dev_sets[s % len(dev_sets)], reduce=False)
+            run_step(model, bucket, cams[view_of(s, my_views)], dev_sets[s % len(dev_sets)], reduce=False, optimizer=optimizer)
         torch.cuda.synchronize()
+        model.__dict__["_raster_stats"] = None
         for name, a, b in R.STAGE_EVENTS:
             stages[name] = stages.get(name, 0.0) + a.elapsed_time(b) / n_prof
         R.STAGE_EVENTS = None
-        out = model.raster_out
-        info = out.info
+        walked_f, kept_f, walked_b, kept_b = (x / n_prof for x in stats_dev.tolist())
+        info = model.raster_out.info
         I = int(info["n_isects_dev"])
-        to = info["tile_offsets"].long()
-        tiles_x = info["tile_width"]
         H, W = args.height, args.width
-        last = info["last_ids"].long()
-        # intersections actually composited: per tile, up to the deepest last_id of its pixels
-        pad_h, pad_w = (-H) % 16, (-W) % 16
-        lp = torch.nn.functional.pad(last, (0, pad_w, 0, pad_h), value=-1)
-        tmax = lp.view((H + pad_h) // 16, 16, (W + pad_w) // 16, 16).amax(dim=(1, 3)).reshape(-1)
-        i_eff = int(torch.clamp(torch.minimum(tmax + 1, to[1:]) - to[:-1], min=0).sum())
+        i_eff = int(kept_b)  # (tile, Gaussian) pairs the backward composites: kept by the tile filter up to the deepest last id
         cn = 1 if normals else 0
         P = H * W
         from json import load as _jl
@@ -457,7 +523,7 @@ def main():
         G = 48 + 12 * cn
         alg = {
             "raster_bwd": (28 + 12 * cn) * P + (20 + 12 * cn) * P + (4 + 44 + 12 * cn) * i_eff + G * i_eff,
-            "raster_fwd": (4 + 44 + 12 * cn) * i_eff + (28 + 12 * cn) * P,
+            "raster_fwd": (4 + 44 + 12 * cn) * int(kept_f) + (28 + 12 * cn) * P,
             "bin_sort": 44 * I,
             "project_fwd": (44 + 32 + 12 * 16 + 12 + 12 * cn) * args.n_gauss,
             "project_bwd": (G + 44 + 44 + 12 * 16) * args.n_gauss,
@@ -472,7 +538,9 @@ def main():
             traffic = t.get(key, {}).get("dram_bytes_per_launch")
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
-                "n_isects": I, "n_isects_composited": i_eff, "ms_per_launch": stages[dom]}
+                "n_isects": I, "n_isects_composited": i_eff, "ms_per_launch": stages[dom],
+                "list_entries_walked_fwd": int(walked_f), "kept_by_tile_filter_fwd": int(kept_f),
+                "list_entries_walked_bwd": int(walked_b), "list_tile_px": info["list_tile"]}
 
     cpu = None
     if rank == 0 and not args.skip_cpu_baseline and world == 1:
@@ -486,7 +554,7 @@ def main():
             "gpu_launches": launches["handwritten"],
             "gpu_launches_note": f"hand-written dnr kernels counted at the C-ABI calls of the timed region; the same calls ran "
                                  f"{launches['cub']} cub radix-sort/scan passes (compiled into libdnr_b200.so)",
-            "roofline": roof, "stages_ms": stages, "cpu_baseline": cpu, "last_loss": losses[-1] if losses else None,
+            "roofline": roof, "stages_ms": stages, "epochs": epochs, "cpu_baseline": cpu, "last_loss": losses[-1] if losses else None,
             "cuda_graph": graph_info, "isect_capacity_report": {str(k): v for k, v in R.capacity_report().items()},
         }
         print(json.dumps(line), flush=True)

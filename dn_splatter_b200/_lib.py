@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(HERE, "libdnr_b200.so")
 FLAG_ACTIVATED, FLAG_ANTIALIASED, FLAG_NORMALS, FLAG_ACCUMULATE, FLAG_EXACT_LISTS = 1, 2, 4, 8, 16
 FLAG_HOST_CAMERA = 32
 FLAG_COMPACT_BWD = 64
+FLAG_TOUCHED_BWD = 128
+LOSS_FUSED_BWD, LOSS_IMG_U8, LOSS_NORMAL_U8, LOSS_EDGE_FROM_IMAGE = 1, 2, 4, 8
 REC_FLOATS, REC_FLOATS_N, GRAD_FLOATS = 12, 16, 16
 DEPTH_LOSS_TYPES = {None: 0, "EdgeAwareLogL1": 1, "LogL1": 2, "L1": 3, "MSE": 4}
 
@@ -23,7 +25,7 @@ class DnrArgs(C.Structure):
 
     _fields_ = [
         ("n_gauss", _i), ("width", _i), ("height", _i), ("tile_size", _i), ("sh_degree", _i), ("sh_bases", _i),
-        ("flags", C.c_uint32), ("reserved0", _i),
+        ("flags", C.c_uint32), ("list_shift", _i),
         ("near_plane", _f), ("far_plane", _f), ("eps2d", _f), ("radius_clip", _f),
         ("background", _f * 3), ("reserved1", _f),
         ("n_isects", C.c_int64),
@@ -41,6 +43,7 @@ class DnrArgs(C.Structure):
         ("depth_lambda", _f), ("depth_tolerance", _f), ("depth_loss_type", _i), ("use_normal_loss", _i),
         ("host_cam", _f * 32),
         ("depth_order", _p),
+        ("loss_flags", C.c_uint32), ("variant", _i), ("gt_image", _p), ("v_l1", _p), ("touched", _p), ("stats", _p),
     ]
 
 

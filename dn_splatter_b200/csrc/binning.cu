@@ -16,6 +16,12 @@
 //   4. STABLE radix sort of the I pairs on the tile-id bits only (13-15 bits, 16-bit keys): within a
 //      tile the depth order of step 1 survives, so the list equals gsplat's sort by (tile, depth, id);
 //   5. tile offsets from the sorted tile ids.
+//
+// Granularity (round 2): the lists are kept per SUPERTILE of (16 << list_shift)^2 pixels.  Only ~7 % of the pairs of a
+// per-tile list are ever composited (pixels saturate long before the list ends), so emitting and sorting per-tile pairs
+// was the largest waste of the step (11.5 M pairs at 1 M Gaussians / 1080p).  With 64-pixel supertiles 4-5x fewer pairs
+// are emitted and sorted; each 16x16 tile then filters the chunks of its supertile's list that it actually walks
+// (dnr_tile_hit in csrc/raster.cu).  list_shift = 0 keeps one list per tile (gsplat's lists with DNR_FLAG_EXACT_LISTS).
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
 
@@ -65,11 +71,11 @@ ScanWs carve_scan(void* base, int32_t n) {
   return w;
 }
 
-// the padding key has all bits set: sort one bit more than the tile ids need so it lands behind every tile
+// the padding key is n_tiles (one past the last list id), so `tile_bits` = bits of the value n_tiles
 template <typename KeyT>
 inline int sort_end_bit(int tile_bits) {
   const int full = (int)(8 * sizeof(KeyT));
-  return tile_bits + 1 < full ? tile_bits + 1 : full;
+  return tile_bits < full ? tile_bits : full;
 }
 
 template <typename KeyT>
@@ -100,9 +106,9 @@ SortWs<KeyT> carve_sort(void* base, int64_t n_isects, int tile_bits) {
   return w;
 }
 
-inline int tile_bits_for(int n_tiles) {
+inline int tile_bits_for(int n_tiles) {  // bits needed to represent the values 0..n_tiles (n_tiles = the padding key)
   int b = 1;
-  while ((1 << b) < n_tiles) ++b;
+  while ((1 << b) <= n_tiles) ++b;
   return b;
 }
 
@@ -119,6 +125,18 @@ struct HitGauss {
   float mx, my, A, B, invA, bac, twoAL, ex_max, ey_max, ey_star;
 };
 
+// box of list tiles (edge `ts` pixels) a projected Gaussian overlaps; ts = 16 reproduces dnr_tile_box bit for bit
+__device__ __forceinline__ void list_box(float mx, float my, int radius, int ts, int tiles_x, int tiles_y, int& x0, int& y0,
+                                         int& x1, int& y1) {
+  if (ts == DNR_TILE) { dnr_tile_box(mx, my, radius, tiles_x, tiles_y, x0, y0, x1, y1); return; }
+  const float inv = 1.0f / (float)ts;  // power of two: exact
+  const float r = (float)radius * inv, tcx = mx * inv, tcy = my * inv;
+  x0 = min(max((int)floorf(tcx - r), 0), tiles_x);
+  y0 = min(max((int)floorf(tcy - r), 0), tiles_y);
+  x1 = min(max((int)ceilf(tcx + r), 0), tiles_x);
+  y1 = min(max((int)ceilf(tcy + r), 0), tiles_y);
+}
+
 __device__ __forceinline__ HitGauss load_hit_gauss(const DnrArgs& a, const int32_t* __restrict__ order, int i, int tiles_x,
                                                    int tiles_y) {
   HitGauss h;
@@ -130,7 +148,7 @@ __device__ __forceinline__ HitGauss load_hit_gauss(const DnrArgs& a, const int32
     if (h.radius > 0) {
       h.mx = a.means2d[h.g * 2 + 0]; h.my = a.means2d[h.g * 2 + 1];
       int x1, y1;
-      dnr_tile_box(h.mx, h.my, h.radius, tiles_x, tiles_y, h.x0, h.y0, x1, y1);
+      list_box(h.mx, h.my, h.radius, DNR_TILE << a.list_shift, tiles_x, tiles_y, h.x0, h.y0, x1, y1);
       h.nx = x1 - h.x0;
       h.ny = y1 - h.y0;
       if (!(a.flags & DNR_FLAG_EXACT_LISTS)) {
@@ -165,11 +183,11 @@ __device__ __forceinline__ HitGauss bcast_hit_gauss(const HitGauss& h, int src) 
 }
 
 // Tiles [lo, hi) of tile-row `ty` that the Gaussian can reach (empty when hi <= lo); `exact` keeps the whole box row.
-__device__ __forceinline__ void row_span(const HitGauss& h, int ty, bool exact, int& lo, int& hi) {
+__device__ __forceinline__ void row_span(const HitGauss& h, int ty, bool exact, int ts, int& lo, int& hi) {
   lo = h.x0; hi = h.x0 + h.nx;
   if (exact) return;
-  float e0 = ((float)(ty * DNR_TILE) + 0.5f) - h.my - 0.01f;
-  float e1 = ((float)(ty * DNR_TILE + DNR_TILE - 1) + 0.5f) - h.my + 0.01f;
+  float e0 = ((float)(ty * ts) + 0.5f) - h.my - 0.01f;
+  float e1 = ((float)(ty * ts + ts - 1) + 0.5f) - h.my + 0.01f;
   if (e0 > h.ey_max || e1 < -h.ey_max) { hi = lo; return; }
   e0 = fmaxf(e0, -h.ey_max); e1 = fminf(e1, h.ey_max);
   const float s0 = sqrtf(fmaxf(fmaf(h.bac, e0 * e0, h.twoAL), 0.f)), s1 = sqrtf(fmaxf(fmaf(h.bac, e1 * e1, h.twoAL), 0.f));
@@ -179,9 +197,10 @@ __device__ __forceinline__ void row_span(const HitGauss& h, int ty, bool exact, 
   if (-h.ey_star >= e0 && -h.ey_star <= e1) xmin = -h.ex_max;
   xmax = xmax + 0.01f + 1e-5f * fabsf(xmax);
   xmin = xmin - 0.01f - 1e-5f * fabsf(xmin);
-  // tile tx holds pixel centres [16 tx + 0.5, 16 tx + 15.5]
-  const int t_lo = (int)ceilf((h.mx + xmin - 15.5f) * (1.0f / DNR_TILE));
-  const int t_hi = (int)floorf((h.mx + xmax - 0.5f) * (1.0f / DNR_TILE)) + 1;
+  // tile tx holds pixel centres [ts tx + 0.5, ts tx + ts - 0.5]
+  const float inv = 1.0f / (float)ts;
+  const int t_lo = (int)ceilf((h.mx + xmin - ((float)ts - 0.5f)) * inv);
+  const int t_hi = (int)floorf((h.mx + xmax - 0.5f) * inv) + 1;
   lo = max(lo, t_lo); hi = min(hi, t_hi);
 }
 
@@ -192,10 +211,11 @@ __global__ void __launch_bounds__(256) count_kernel(const DnrArgs a, const int32
   if (i > a.n_gauss) return;
   const HitGauss h = load_hit_gauss(a, order, i, tiles_x, tiles_y);
   const bool exact = (a.flags & DNR_FLAG_EXACT_LISTS) != 0;
+  const int ts = DNR_TILE << a.list_shift;
   int cnt = 0;
   for (int r = 0; r < h.ny; ++r) {
     int lo, hi;
-    row_span(h, h.y0 + r, exact, lo, hi);
+    row_span(h, h.y0 + r, exact, ts, lo, hi);
     cnt += max(hi - lo, 0);
   }
   counts[i] = (i < a.n_gauss) ? cnt : 0;
@@ -224,6 +244,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_
   const int64_t my_end = loader ? isect_start[base + lane + 1] : 0;
   const int64_t cap = a.n_isects;
   const bool exact = (a.flags & DNR_FLAG_EXACT_LISTS) != 0;
+  const int ts = DNR_TILE << a.list_shift;
   unsigned todo = __ballot_sync(0xffffffffu, my_end > my_start);
   while (todo) {
     const int src = __ffs(todo) - 1;
@@ -233,7 +254,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_
     for (int r0 = 0; r0 < h.ny; r0 += 32) {
       const int r = r0 + lane;
       int lo = 0, hi = 0;
-      if (r < h.ny) row_span(h, h.y0 + r, exact, lo, hi);
+      if (r < h.ny) row_span(h, h.y0 + r, exact, ts, lo, hi);
       const int len = max(hi - lo, 0);
       int incl = len;  // inclusive warp scan of the span lengths
 #pragma unroll
@@ -277,10 +298,10 @@ __global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_
 // Pads [count, capacity) with the maximal key so a fixed-size sort leaves them at the end.
 template <typename KeyT>
 __global__ void __launch_bounds__(256) pad_kernel(KeyT* __restrict__ keys, int32_t* __restrict__ gids,
-                                                 const int64_t* __restrict__ n_isects_dev, int64_t cap) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < cap && i >= *n_isects_dev) {
-    keys[i] = (KeyT)~(KeyT)0;
+                                                 const int64_t* __restrict__ n_isects_dev, int64_t cap, KeyT pad_key) {
+  // only the tail [count, capacity) is touched: a small fixed grid strides over it
+  for (int64_t i = *n_isects_dev + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
+    keys[i] = pad_key;
     gids[i] = 0;
   }
 }
@@ -309,7 +330,7 @@ __global__ void __launch_bounds__(256) offsets_kernel(const KeyT* __restrict__ k
 
 template <typename KeyT>
 int bin_sort_impl(const DnrArgs* a, cudaStream_t s, int n_tiles, int tile_bits) {
-  const int tiles_x = dnr_tiles_x(a), tiles_y = dnr_tiles_y(a);
+  const int tiles_x = dnr_stiles_x(a), tiles_y = dnr_stiles_y(a);
   ScanWs sw = carve_scan(a->ws_scan, a->n_gauss);
   const int64_t cap = a->n_isects;
   SortWs<KeyT> w = carve_sort<KeyT>(a->ws_sort, cap, tile_bits);
@@ -318,7 +339,7 @@ int bin_sort_impl(const DnrArgs* a, cudaStream_t s, int n_tiles, int tile_bits) 
     emit_kernel<KeyT><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(*a, sw.order, sw.isect_start, w.keys_in, w.gids_in,
                                                                           tiles_x, tiles_y);
     DNR_CHECK_LAUNCH();
-    pad_kernel<KeyT><<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(w.keys_in, w.gids_in, a->n_isects_dev, cap);
+    pad_kernel<KeyT><<<148 * 2, 256, 0, s>>>(w.keys_in, w.gids_in, a->n_isects_dev, cap, (KeyT)n_tiles);
     DNR_CHECK_LAUNCH();
     size_t bytes = w.cub_bytes;
     const int end_bit = sort_end_bit<KeyT>(tile_bits);
@@ -346,6 +367,8 @@ extern "C" const int32_t* dnr_depth_order_ptr(void* ws_scan, int32_t n_gauss) {
 extern "C" int dnr_bin_scan(const DnrArgs* a, void* stream, int64_t* n_isects_host) {
   if (!a) return DNR_E_NULL;
   if (a->n_gauss <= 0 || a->width <= 0 || a->height <= 0) return DNR_E_SIZE;
+  if (a->list_shift < 0 || a->list_shift > 3) return DNR_E_OPTION;
+  if ((a->flags & DNR_FLAG_EXACT_LISTS) && a->list_shift != 0) return DNR_E_OPTION;
   if (!a->ws_scan || !a->depth_keys || !a->tiles_per_gauss || !a->n_isects_dev || !a->radii || !a->means2d) return DNR_E_NULL;
   if (!(a->flags & DNR_FLAG_EXACT_LISTS) && (!a->conics || !a->cull_lim)) return DNR_E_NULL;
   cudaStream_t s = (cudaStream_t)stream;
@@ -358,7 +381,7 @@ extern "C" int dnr_bin_scan(const DnrArgs* a, void* stream, int64_t* n_isects_ho
                                            (const int32_t*)w.iota, w.order, n, 0, 32, s));
   {
     const int64_t threads = (int64_t)n + 1;  // one lane per Gaussian (+ the terminating zero)
-    count_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(*a, w.order, w.counts, dnr_tiles_x(a), dnr_tiles_y(a));
+    count_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(*a, w.order, w.counts, dnr_stiles_x(a), dnr_stiles_y(a));
     DNR_CHECK_LAUNCH();
   }
   auto it = thrust::make_transform_iterator((const int32_t*)w.counts, ToI64());
@@ -379,7 +402,7 @@ extern "C" size_t dnr_bin_sort_workspace_bytes(int32_t n_gauss, int64_t n_isects
   (void)n_gauss;
   if (n_isects < 0 || n_tiles <= 0) return 0;
   const int bits = tile_bits_for(n_tiles);
-  if (n_tiles <= 65536) return carve_sort<uint16_t>(nullptr, n_isects, bits).total;
+  if (n_tiles < 65536) return carve_sort<uint16_t>(nullptr, n_isects, bits).total;
   return carve_sort<uint32_t>(nullptr, n_isects, bits).total;
 }
 
@@ -390,9 +413,11 @@ extern "C" int dnr_bin_sort(const DnrArgs* a, void* stream) {
   if (!a->ws_scan || !a->ws_sort || !a->tile_offsets || !a->means2d || !a->radii || !a->n_isects_dev) return DNR_E_NULL;
   if (!(a->flags & DNR_FLAG_EXACT_LISTS) && (!a->conics || !a->cull_lim)) return DNR_E_NULL;
   if (a->n_isects > 0 && !a->flatten_ids) return DNR_E_NULL;
-  const int n_tiles = dnr_tiles_x(a) * dnr_tiles_y(a);
+  if (a->list_shift < 0 || a->list_shift > 3) return DNR_E_OPTION;
+  if ((a->flags & DNR_FLAG_EXACT_LISTS) && a->list_shift != 0) return DNR_E_OPTION;
+  const int n_tiles = dnr_stiles_x(a) * dnr_stiles_y(a);  // number of lists
   const int bits = tile_bits_for(n_tiles);
   cudaStream_t s = (cudaStream_t)stream;
-  if (n_tiles <= 65536) return bin_sort_impl<uint16_t>(a, s, n_tiles, bits);
+  if (n_tiles < 65536) return bin_sort_impl<uint16_t>(a, s, n_tiles, bits);
   return bin_sort_impl<uint32_t>(a, s, n_tiles, bits);
 }

@@ -8,6 +8,7 @@
 //   loss_fwd / loss_bwd   DNRegularization depth + normal terms (regularization_strategy.py:146-193;
 //                         losses.py:155-224 L1/LogL1/EdgeAwareLogL1, :279-295 TVLoss)
 #include "common.cuh"
+#include "loss_common.cuh"
 
 namespace {
 
@@ -88,13 +89,7 @@ __global__ void __launch_bounds__(256) normal_from_depth_kernel(const DnrArgs a)
   a.out_surface_normal[pix * 3 + 2] = n[2];
 }
 
-__device__ __forceinline__ float rgb_edge(const float* rgb, int p, int q) {
-  const float g = (fabsf(rgb[p * 3 + 0] - rgb[q * 3 + 0]) + fabsf(rgb[p * 3 + 1] - rgb[q * 3 + 1])) +
-                  fabsf(rgb[p * 3 + 2] - rgb[q * 3 + 2]);
-  return expf(-(g / 3.0f));
-}
-
-__device__ __forceinline__ float sgn(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+__device__ __forceinline__ float sgn(float x) { return sgnf(x); }
 
 // per-pixel depth-term pieces: value (for the type) and d(value)/d(pred)
 __device__ __forceinline__ void depth_term(int type, float d, float g, float& val, float& dval) {
@@ -116,8 +111,8 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(const DnrArgs a) {
       float val, dval;
       depth_term(a.depth_loss_type, a.out_depth[p], a.gt_depth[p], val, dval);
       if (a.depth_loss_type == 1) {
-        if (j < W - 1) { s[0] = rgb_edge(a.gt_rgb, p, p + 1) * val; s[1] = 1.f; }
-        if (i < H - 1) { s[2] = rgb_edge(a.gt_rgb, p, p + W) * val; s[3] = 1.f; }
+        if (j < W - 1) { s[0] = edge_weight(a, p, p + 1) * val; s[1] = 1.f; }
+        if (i < H - 1) { s[2] = edge_weight(a, p, p + W) * val; s[3] = 1.f; }
       } else {
         s[0] = val; s[1] = 1.f;
       }
@@ -126,7 +121,7 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(const DnrArgs a) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float n = a.out_normal[p * 3 + c];
-        s[4] += fabsf(n - a.gt_normal[p * 3 + c]);
+        s[4] += fabsf(n - gt_normal_at(a, p * 3 + c));
         if (j < W - 1) s[5] += fabsf(n - a.out_normal[(p + 1) * 3 + c]);
         if (i < H - 1) s[6] += fabsf(n - a.out_normal[(p + W) * 3 + c]);
       }
@@ -161,8 +156,8 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const DnrArgs a, float* _
       const float scale = vl * (1.0f + a.depth_lambda);  // quirk B6: depth_loss += lambda * depth_loss
       if (a.depth_loss_type == 1) {
         float w = 0.f;
-        if (j < W - 1) w += rgb_edge(a.gt_rgb, p, p + 1) / a.loss_partials[1];
-        if (i < H - 1) w += rgb_edge(a.gt_rgb, p, p + W) / a.loss_partials[3];
+        if (j < W - 1) w += edge_weight(a, p, p + 1) / a.loss_partials[1];
+        if (i < H - 1) w += edge_weight(a, p, p + W) / a.loss_partials[3];
         g = scale * dval * w;
       } else {
         g = scale * dval / a.loss_partials[1];
@@ -179,7 +174,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const DnrArgs a, float* _
       float g = 0.f;
       if (a.use_normal_loss) {
         const float n = a.out_normal[p * 3 + c];
-        g = sgn(n - a.gt_normal[p * 3 + c]) * inv_l1;
+        g = sgn(n - gt_normal_at(a, p * 3 + c)) * inv_l1;
         if (j < W - 1) g += sgn(n - a.out_normal[(p + 1) * 3 + c]) * inv_tx;
         if (j > 0) g -= sgn(a.out_normal[(p - 1) * 3 + c] - n) * inv_tx;
         if (i < H - 1) g += sgn(n - a.out_normal[(p + W) * 3 + c]) * inv_ty;
@@ -310,7 +305,8 @@ extern "C" int dnr_loss_fwd(const DnrArgs* a, void* stream) {
   if (a->depth_loss_type < 0 || a->depth_loss_type > 4) return DNR_E_OPTION;
   if (!a->loss_partials) return DNR_E_NULL;
   if (a->depth_loss_type != 0 && (!a->out_depth || !a->gt_depth)) return DNR_E_NULL;
-  if (a->depth_loss_type == 1 && !a->gt_rgb) return DNR_E_NULL;
+  if (a->depth_loss_type == 1 && !((a->loss_flags & DNR_LOSS_EDGE_FROM_IMAGE) ? a->gt_image : (const void*)a->gt_rgb)) return DNR_E_NULL;
+  if ((a->loss_flags & DNR_LOSS_EDGE_FROM_IMAGE) && !(a->loss_flags & DNR_LOSS_IMG_U8)) return DNR_E_OPTION;
   if (a->use_normal_loss && (!a->out_normal || !a->gt_normal)) return DNR_E_NULL;
   cudaStream_t s = (cudaStream_t)stream;
   DNR_CUDA(cudaMemsetAsync(a->loss_partials, 0, 12 * sizeof(float), s));
@@ -327,7 +323,7 @@ extern "C" int dnr_loss_bwd(const DnrArgs* a, float* v_depth_out, float* v_norma
   if (a->depth_loss_type < 0 || a->depth_loss_type > 4) return DNR_E_OPTION;
   if (!a->loss_partials) return DNR_E_NULL;
   if (v_depth_out && a->depth_loss_type != 0 && (!a->out_depth || !a->gt_depth)) return DNR_E_NULL;
-  if (v_depth_out && a->depth_loss_type == 1 && !a->gt_rgb) return DNR_E_NULL;
+  if (v_depth_out && a->depth_loss_type == 1 && !((a->loss_flags & DNR_LOSS_EDGE_FROM_IMAGE) ? a->gt_image : (const void*)a->gt_rgb)) return DNR_E_NULL;
   if (v_normal_out && a->use_normal_loss && (!a->out_normal || !a->gt_normal)) return DNR_E_NULL;
   loss_bwd_kernel<<<img_grid(a), 256, 0, (cudaStream_t)stream>>>(*a, v_depth_out, v_normal_out);
   DNR_CHECK_LAUNCH();

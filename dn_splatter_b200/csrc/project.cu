@@ -354,48 +354,12 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const DnrArgs a) {
 constexpr int PB_THREADS = 128;   // Gaussians per CTA in project_bwd
 constexpr int PB_REST_MAX = 45;    // (16 - 1) * 3 floats of higher-order SH gradient per Gaussian
 
-// The 180 B/Gaussian SH-gradient rows are staged in shared memory (stride 45 words: conflict-free) and written
-// by the whole CTA as one contiguous, coalesced stream instead of 45 strided 4-byte stores per thread.
-// COMPACT (experimental, DNR_FLAG_COMPACT_BWD): slot s of the grid handles Gaussian depth_order[s]; the visible ones
-// come first in that order, so full CTAs do useful work and the tail CTAs leave after one load.  Rows are then
-// scattered, hence accumulate-only.
-template <bool NORMALS, bool COMPACT>
-__global__ void __launch_bounds__(PB_THREADS, 8) project_bwd_kernel(const DnrArgs a) {
-  __shared__ float s_rest[PB_THREADS * PB_REST_MAX];
-  __shared__ unsigned char s_vis[PB_THREADS];
-  __shared__ unsigned char s_list[PB_THREADS];
-  __shared__ int s_gid[COMPACT ? PB_THREADS : 1];
-  __shared__ int s_nvis;
-  const int slot = blockIdx.x * PB_THREADS + threadIdx.x;
-  const bool in_range = slot < a.n_gauss;
-  const int i = COMPACT ? (in_range ? a.depth_order[slot] : 0) : slot;  // Gaussian id
-  if (COMPACT) s_gid[threadIdx.x] = i;
-  const bool acc = COMPACT ? true : (a.flags & DNR_FLAG_ACCUMULATE) != 0;
-  const int nrest = a.sh_bases - 1;
-  const int nrow = nrest * 3;
-  const int radius = in_range ? a.radii[i] : 0;
-  const bool visible = radius > 0;
-  s_vis[threadIdx.x] = visible ? 1 : 0;
-  // means2d.grad / .absgrad (what densification reads) are plain outputs, not accumulators: invisible rows are zero in
-  // every mode (the caller hands in uninitialised buffers)
-  if (in_range && !visible) {
-    if (a.v_means2d) { a.v_means2d[i * 2] = 0.f; a.v_means2d[i * 2 + 1] = 0.f; }
-    if (a.v_means2d_abs) { a.v_means2d_abs[i * 2] = 0.f; a.v_means2d_abs[i * 2 + 1] = 0.f; }
-  }
-  float* srow = s_rest + threadIdx.x * PB_REST_MAX;
-  // visible rows are fully written by the SH section below; invisible rows are only read by the dense-overwrite path
-  if (!visible && !acc) {
-#pragma unroll
-    for (int k = 0; k < PB_REST_MAX; ++k) srow[k] = 0.f;
-  }
-  if (acc && !__syncthreads_or(visible ? 1 : 0)) return;  // nothing to accumulate from this CTA
-  float vm[3] = {0, 0, 0}, vq[4] = {0, 0, 0, 0}, vs[3] = {0, 0, 0}, vo = 0.f, vdc[3] = {0, 0, 0};
-  if (in_range && !visible && !acc) {
-    for (int k = 0; k < 3; ++k) { a.v_means[i * 3 + k] = 0.f; a.v_scales[i * 3 + k] = 0.f; a.v_sh_dc[i * 3 + k] = 0.f; }
-    for (int k = 0; k < 4; ++k) a.v_quats[i * 4 + k] = 0.f;
-    a.v_opacities[i] = 0.f;
-  }
-  if (visible) {
+// Parameter gradients of ONE visible Gaussian from its raster-gradient record: gsplat fully_fused_projection_bwd +
+// spherical_harmonics bwd + activation / normal chain rules.  The 3*(sh_bases-1) higher-order SH gradients go to `srow`
+// (shared memory staging, written out by the caller); the rest is returned in registers.
+template <bool NORMALS>
+__device__ __forceinline__ void project_bwd_gauss(const DnrArgs& a, int i, int nrest, float* srow, float vm[3], float vq[4],
+                                                  float vs[3], float& vo, float vdc[3]) {
   Cam cam;
   load_cam(a, cam);
   Geo g;
@@ -583,6 +547,50 @@ __global__ void __launch_bounds__(PB_THREADS, 8) project_bwd_kernel(const DnrArg
       vm[2] += (vu[2] - uz * dp) * inorm;
     }
   }
+}
+
+// The 180 B/Gaussian SH-gradient rows are staged in shared memory (stride 45 words: conflict-free) and written
+// by the whole CTA as one contiguous, coalesced stream instead of 45 strided 4-byte stores per thread.
+// COMPACT (experimental, DNR_FLAG_COMPACT_BWD): slot s of the grid handles Gaussian depth_order[s]; the visible ones
+// come first in that order, so full CTAs do useful work and the tail CTAs leave after one load.  Rows are then
+// scattered, hence accumulate-only.
+template <bool NORMALS, bool COMPACT>
+__global__ void __launch_bounds__(PB_THREADS, 8) project_bwd_kernel(const DnrArgs a) {
+  __shared__ float s_rest[PB_THREADS * PB_REST_MAX];
+  __shared__ unsigned char s_vis[PB_THREADS];
+  __shared__ unsigned char s_list[PB_THREADS];
+  __shared__ int s_gid[COMPACT ? PB_THREADS : 1];
+  __shared__ int s_nvis;
+  const int slot = blockIdx.x * PB_THREADS + threadIdx.x;
+  const bool in_range = slot < a.n_gauss;
+  const int i = COMPACT ? (in_range ? a.depth_order[slot] : 0) : slot;  // Gaussian id
+  if (COMPACT) s_gid[threadIdx.x] = i;
+  const bool acc = COMPACT ? true : (a.flags & DNR_FLAG_ACCUMULATE) != 0;
+  const int nrest = a.sh_bases - 1;
+  const int nrow = nrest * 3;
+  const int radius = in_range ? a.radii[i] : 0;
+  const bool visible = radius > 0;
+  s_vis[threadIdx.x] = visible ? 1 : 0;
+  // means2d.grad / .absgrad (what densification reads) are plain outputs, not accumulators: invisible rows are zero in
+  // every mode (the caller hands in uninitialised buffers)
+  if (in_range && !visible) {
+    if (a.v_means2d) { a.v_means2d[i * 2] = 0.f; a.v_means2d[i * 2 + 1] = 0.f; }
+    if (a.v_means2d_abs) { a.v_means2d_abs[i * 2] = 0.f; a.v_means2d_abs[i * 2 + 1] = 0.f; }
+  }
+  float* srow = s_rest + threadIdx.x * PB_REST_MAX;
+  // visible rows are fully written by the SH section below; invisible rows are only read by the dense-overwrite path
+  if (!visible && !acc) {
+#pragma unroll
+    for (int k = 0; k < PB_REST_MAX; ++k) srow[k] = 0.f;
+  }
+  if (acc && !__syncthreads_or(visible ? 1 : 0)) return;  // nothing to accumulate from this CTA
+  float vm[3] = {0, 0, 0}, vq[4] = {0, 0, 0, 0}, vs[3] = {0, 0, 0}, vo = 0.f, vdc[3] = {0, 0, 0};
+  if (in_range && !visible && !acc) {
+    for (int k = 0; k < 3; ++k) { a.v_means[i * 3 + k] = 0.f; a.v_scales[i * 3 + k] = 0.f; a.v_sh_dc[i * 3 + k] = 0.f; }
+    for (int k = 0; k < 4; ++k) a.v_quats[i * 4 + k] = 0.f;
+    a.v_opacities[i] = 0.f;
+  }
+  if (visible) project_bwd_gauss<NORMALS>(a, i, nrest, srow, vm, vq, vs, vo, vdc);
   if (acc) {
     for (int k = 0; k < 3; ++k) { a.v_means[i * 3 + k] += vm[k]; a.v_scales[i * 3 + k] += vs[k]; a.v_sh_dc[i * 3 + k] += vdc[k]; }
     for (int k = 0; k < 4; ++k) a.v_quats[i * 4 + k] += vq[k];
@@ -592,7 +600,6 @@ __global__ void __launch_bounds__(PB_THREADS, 8) project_bwd_kernel(const DnrArg
     for (int k = 0; k < 4; ++k) a.v_quats[i * 4 + k] = vq[k];
     a.v_opacities[i] = vo;
   }
-  }  // visible
   __syncthreads();
   if (nrest > 0) {
     const int g0 = blockIdx.x * PB_THREADS;
@@ -622,6 +629,75 @@ __global__ void __launch_bounds__(PB_THREADS, 8) project_bwd_kernel(const DnrArg
         else out[(size_t)r * nrow + k] += s_rest[r * PB_REST_MAX + k];
       }
     }
+  }
+}
+
+// DNR_FLAG_TOUCHED_BWD: only Gaussians that received a raster gradient are processed (touched[g] != 0, written by
+// dnr_raster_bwd).  On the 1 M-Gaussian / 1080p scene ~40 % are visible but only ~10 % are ever composited before the
+// pixels saturate; the dense kernel above still pays a latency-bound pass over every warp that holds one visible
+// Gaussian.  Here a CTA scans the flags of PB_SCAN consecutive Gaussians (coalesced bytes), compacts the touched ids in
+// shared memory and then runs the per-Gaussian backward with every lane busy; the 180 B SH rows are staged in shared
+// memory and accumulated row by row (each row is a contiguous span).  Accumulate-only: the caller pre-zeroes the
+// gradient buffers (and v_means2d / v_means2d_abs).
+constexpr int PB_SCAN = 1024;
+
+template <bool NORMALS>
+__global__ void __launch_bounds__(PB_THREADS, 8) project_bwd_touched_kernel(const DnrArgs a) {
+  __shared__ float s_rest[PB_THREADS * PB_REST_MAX];
+  __shared__ int s_ids[PB_SCAN];
+  __shared__ int s_n;
+  const int tid = threadIdx.x;
+  const int base = blockIdx.x * PB_SCAN;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  {
+    const int n_here = min(PB_SCAN, a.n_gauss - base);
+    const uint8_t* fl = a.touched + base;
+    // 8 flags per thread and step; `base` is a multiple of 1024, so the 8-byte loads are aligned
+    for (int k = tid * 8; k < n_here; k += PB_THREADS * 8) {
+      unsigned long long w = 0;
+      if (k + 8 <= n_here) {
+        w = *reinterpret_cast<const unsigned long long*>(fl + k);
+      } else {
+        for (int b = 0; k + b < n_here; ++b) w |= (unsigned long long)fl[k + b] << (8 * b);
+      }
+      while (w) {
+        const int b = (__ffsll((long long)w) - 1) >> 3;
+        s_ids[atomicAdd(&s_n, 1)] = base + k + b;
+        w &= ~(0xffull << (8 * b));
+      }
+    }
+  }
+  __syncthreads();
+  const int n_touched = s_n;
+  const int nrest = a.sh_bases - 1;
+  const int nrow = nrest * 3;
+  float* srow = s_rest + tid * PB_REST_MAX;
+  for (int off = 0; off < n_touched; off += PB_THREADS) {
+    const int slot = off + tid;
+    const bool active = slot < n_touched;
+    if (active) {
+      const int i = s_ids[slot];
+      float vm[3] = {0, 0, 0}, vq[4] = {0, 0, 0, 0}, vs[3] = {0, 0, 0}, vo = 0.f, vdc[3] = {0, 0, 0};
+      if (a.radii[i] > 0) {
+        project_bwd_gauss<NORMALS>(a, i, nrest, srow, vm, vq, vs, vo, vdc);
+      } else {
+        for (int k = 0; k < nrow; ++k) srow[k] = 0.f;
+      }
+      for (int k = 0; k < 3; ++k) { a.v_means[i * 3 + k] += vm[k]; a.v_scales[i * 3 + k] += vs[k]; a.v_sh_dc[i * 3 + k] += vdc[k]; }
+      for (int k = 0; k < 4; ++k) a.v_quats[i * 4 + k] += vq[k];
+      a.v_opacities[i] += vo;
+    }
+    __syncthreads();
+    if (nrest > 0) {
+      const int rows = min(PB_THREADS, n_touched - off);
+      const int total = rows * nrow;
+      for (int e = tid; e < total; e += PB_THREADS) {
+        const int r = e / nrow, k = e - r * nrow;
+        a.v_sh_rest[(size_t)s_ids[off + r] * nrow + k] += s_rest[r * PB_REST_MAX + k];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -663,7 +739,13 @@ extern "C" int dnr_project_bwd(const DnrArgs* a, void* stream) {
   if (a->sh_bases > 16) return DNR_E_OPTION;
   const int block = PB_THREADS, grid = (a->n_gauss + block - 1) / block;
   cudaStream_t s = (cudaStream_t)stream;
-  if (a->flags & DNR_FLAG_COMPACT_BWD) {
+  if (a->flags & DNR_FLAG_TOUCHED_BWD) {
+    if (!a->touched) return DNR_E_NULL;
+    if (!(a->flags & DNR_FLAG_ACCUMULATE)) return DNR_E_OPTION;  // scattered rows: the caller pre-zeroes and accumulates
+    const int tgrid = (a->n_gauss + PB_SCAN - 1) / PB_SCAN;
+    if (normals) project_bwd_touched_kernel<true><<<tgrid, block, 0, s>>>(*a);
+    else project_bwd_touched_kernel<false><<<tgrid, block, 0, s>>>(*a);
+  } else if (a->flags & DNR_FLAG_COMPACT_BWD) {
     if (!a->depth_order) return DNR_E_NULL;
     if (!(a->flags & DNR_FLAG_ACCUMULATE)) return DNR_E_OPTION;  // scattered rows: the caller pre-zeroes and accumulates
     if (normals) project_bwd_kernel<true, true><<<grid, block, 0, s>>>(*a);

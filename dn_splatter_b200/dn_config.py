@@ -31,9 +31,10 @@ METHODS: Dict[str, Dict] = {
         "description": "AGS-Mesh: adaptive Gaussian splatting and meshing",
         "model": lambda: DNSplatterModelConfig(regularization_strategy="ags-mesh"),
     },
-    "dn-splatter-big": {  # dn_config.py:137-198: lower cull threshold, keep densifying
+    "dn-splatter-big": {  # dn_config.py:137-198 (:150-153): lower cull threshold, no culling after stop_split_at
         "description": "DN-Splatter Big variant",
-        "model": lambda: DNSplatterModelConfig(regularization_strategy="dn-splatter", cull_alpha_thresh=0.005),
+        "model": lambda: DNSplatterModelConfig(regularization_strategy="dn-splatter", cull_alpha_thresh=0.005,
+                                               continue_cull_post_densification=False),
     },
 }
 TRAINER_DEFAULTS = dict(steps_per_eval_image=500, steps_per_eval_batch=500, steps_per_save=1000000,

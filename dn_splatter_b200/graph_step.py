@@ -4,7 +4,9 @@ Python per view collapse into one cudaGraphLaunch, which makes the step immune t
 inter-kernel launch gaps.
 
 What makes the step capturable (see rasterize.py / dn_model.py):
-  * `fixed_capacity`: intersection buffers sized once (1.15 x the largest count seen), no count read-back;
+  * `fixed_capacity`: intersection buffers sized once (1.15 x the largest count seen), no count read-back inside the
+    graph; after every replay the view's count is copied to pinned memory asynchronously and checked at the NEXT call
+    (and by `check_capacity()`): a replay that needed more slots raises DnrCapacityError — call `recapture()` and redo;
   * the camera lives in static device tensors (viewmat, K, c2w) that `load_camera` refreshes with one small
     pinned H2D copy before each replay (resolution must not change between replays);
   * the supervision maps live in static device buffers that the caller fills (H2D or D2D) before each replay;
@@ -20,13 +22,16 @@ from typing import Dict, List, Optional
 import torch
 from torch import Tensor
 
-from .rasterize import get_viewmat, suggested_capacity
+from .rasterize import DnrCapacityError, get_viewmat, suggested_capacity
 
 
 class GraphedTrainStep:
     def __init__(self, model, bucket, example_camera, example_batch: Dict[str, Tensor], n_slots: int = 2,
                  capacity: Optional[int] = None, warmup: int = 3):
         assert model.training, "capture the training step in train() mode"
+        if model.config.background_color == "random":
+            raise ValueError("background_color='random' draws a new host-side colour every step; a captured graph would "
+                             "freeze the first one.  Use 'black' / 'white' (or run eagerly).")
         self.model, self.bucket = model, bucket
         dev = model.device
         self.device = dev
@@ -34,7 +39,8 @@ class GraphedTrainStep:
         self.size = (W, H)
         if capacity is None:
             capacity = suggested_capacity(model.num_points, W, H, model.config.predict_normals,
-                                          model.config.exact_isect_lists, dev.index)
+                                          model.config.exact_isect_lists, dev.index,
+                                          0 if model.config.exact_isect_lists else model.config.list_shift)
         if capacity <= 0:
             raise ValueError("no intersection statistics yet: run a few sync_free views first or pass capacity=")
         self.capacity = int(capacity)
@@ -47,10 +53,31 @@ class GraphedTrainStep:
         self.losses = [torch.zeros((), device=dev) for _ in range(n_slots)]
         self.graphs: List[torch.cuda.CUDAGraph] = []
         self._camera = example_camera
+        self._n_slots, self._warmup = n_slots, warmup
+        self._count_dev: List[Optional[Tensor]] = [None] * n_slots   # the graphs' own n_isects_dev tensors
+        self._count_host = torch.zeros(64, dtype=torch.int64).pin_memory()
+        self._count_pending: List = []
+        self._count_slot = 0
+        self.max_count = 0
         for b in self.batches:
             for k, v in example_batch.items():
                 b[k].copy_(v)
         self.load_camera(example_camera)
+        self._capture()
+
+    @staticmethod
+    def _gates(m):
+        """Host-side, step-dependent branches of get_outputs / get_loss_dict that a capture bakes in."""
+        c = m.config
+        return (min(m.step // c.sh_degree_interval, c.sh_degree), bool(c.use_scale_regularization and m.step % 10 == 0),
+                bool(c.use_binary_opacities and m.step > c.warmup_length), m._get_downscale_factor())
+
+    def _capture(self) -> None:
+        model, dev = self.model, self.device
+        self._captured_gates = self._gates(model)
+        warmup, n_slots = self._warmup, self._n_slots
+        self.cam["capacity"] = self.capacity
+        self.graphs = []
         # Autograd graphs of earlier eager steps keep the parameters' AccumulateGrad nodes alive, and those remember the
         # stream they were created on (usually the legacy default stream, which may not take part in a capture):
         # drop the model's cached outputs so the nodes are rebuilt on the warm-up / capture streams.
@@ -86,6 +113,7 @@ class GraphedTrainStep:
             loss = ld["main_loss"] + ld["scale_reg"]
             loss.backward()
             self.losses[slot].copy_(loss.detach())
+            self._count_dev[slot] = m.raster_out.info["n_isects_dev"]
         finally:
             m.__dict__["_graph_cam"] = None
 
@@ -104,6 +132,43 @@ class GraphedTrainStep:
     def __call__(self, camera, slot: int = 0) -> Tensor:
         """Replays the captured step for `camera` on the supervision maps currently in `self.batches[slot]`;
         returns the static loss tensor of that slot (read it asynchronously)."""
+        if self._gates(self.model) != self._captured_gates:
+            raise RuntimeError(f"step-dependent host decisions changed since capture ({self._captured_gates} -> "
+                               f"{self._gates(self.model)}): call recapture()")
+        self.check_capacity()
         self.load_camera(camera)
         self.graphs[slot].replay()
+        host = self._count_host[self._count_slot:self._count_slot + 1]
+        self._count_slot = (self._count_slot + 1) % self._count_host.numel()
+        host.copy_(self._count_dev[slot], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._count_pending.append((host, ev))
+        if len(self._count_pending) >= self._count_host.numel() - 1:
+            self.check_capacity(wait=True)
         return self.losses[slot]
+
+    def check_capacity(self, wait: bool = False) -> None:
+        """Raises DnrCapacityError if a finished replay needed more intersection slots than the graph was captured
+        with (its gradients are truncated: discard them, `recapture()`, replay the view again)."""
+        keep, worst = [], 0
+        for host, ev in self._count_pending:
+            if wait:
+                ev.synchronize()
+            if ev.query():
+                worst = max(worst, int(host.item()))
+            else:
+                keep.append((host, ev))
+        self._count_pending = keep
+        self.max_count = max(self.max_count, worst)
+        if worst > self.capacity:
+            raise DnrCapacityError(f"a replayed view needed {worst} intersection slots, the graph holds {self.capacity}: "
+                                   "its outputs and gradients are truncated; call recapture() and run the view again")
+
+    def recapture(self, capacity: Optional[int] = None) -> None:
+        """Re-captures the step with room for the largest count seen so far (x 1.15) or the given capacity."""
+        need = int(capacity) if capacity else ((int(self.max_count * 1.15) + 4096 + (1 << 19) - 1) >> 19) << 19
+        self.capacity = max(self.capacity, need)
+        self._count_pending = []
+        torch.cuda.synchronize(self.device)
+        self._capture()

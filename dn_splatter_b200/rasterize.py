@@ -24,16 +24,23 @@ from . import _lib as L
 TILE = 16
 
 
+class DnrCapacityError(L.DnrError):
+    """A view needed more intersection slots than its (sync-free / fixed) buffers had: its render and gradients are
+    truncated and must not be used.  The capacity has already been raised; render the view again."""
+
+
 class _CapacityTracker:
     """Sync-free sizing of the intersection buffers: the count of every view is copied to pinned host memory
     asynchronously; capacity for the next view = 1.15 x the largest count seen so far (rounded up).  A view whose
-    count exceeded its capacity was rendered without its farthest intersections; `overflows` counts those."""
+    count exceeded its capacity was rendered without its farthest intersections: that is never silent — the view's
+    own backward (or the next forward, for no-grad renders) raises DnrCapacityError before any gradient is produced."""
 
     SLOTS = 256
 
     def __init__(self):
         self.max_seen, self.overflows, self.pending, self.seeds = 0, 0, [], 0
         self.host, self.slot = None, 0
+        self.unreported = None  # (needed, capacity) of a truncated no-grad view nobody has been told about yet
 
     def seed(self, count: int):
         self.max_seen = max(self.max_seen, count)
@@ -44,9 +51,10 @@ class _CapacityTracker:
         return self.seeds >= 2
 
     def capacity(self) -> int:
-        return ((int(self.max_seen * 1.15) + 4096 + (1 << 21) - 1) >> 21) << 21  # 2M-entry steps: allocator-friendly
+        return ((int(self.max_seen * 1.15) + 4096 + (1 << 19) - 1) >> 19) << 19  # 512K-entry steps: allocator-friendly
 
     def observe(self, n_isects_dev: Tensor, cap: int):
+        """Queues the async read-back of this view's count; returns the ticket its backward checks."""
         if self.host is None:
             self.host = torch.zeros(self.SLOTS, dtype=torch.int64).pin_memory()
         if len(self.pending) >= self.SLOTS - 1:
@@ -56,32 +64,62 @@ class _CapacityTracker:
         host.copy_(n_isects_dev, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        self.pending.append((host, ev, cap))
+        ticket = {"host": host, "event": ev, "cap": cap, "count": None, "checked": False}
+        self.pending.append(ticket)
+        return ticket
+
+    def _resolve(self, t) -> None:
+        if t["count"] is None:
+            t["count"] = int(t["host"].item())
+            self.max_seen = max(self.max_seen, t["count"])
+            if t["count"] > t["cap"]:
+                self.overflows += 1
+                if not t["checked"]:
+                    self.unreported = (t["count"], t["cap"])
 
     def drain(self, wait: bool = False):
         keep = []
-        for host, ev, cap in self.pending:
+        for t in self.pending:
             if wait:
-                ev.synchronize()
-            if ev.query():
-                c = int(host.item())
-                self.max_seen = max(self.max_seen, c)
-                if c > cap:
-                    self.overflows += 1
+                t["event"].synchronize()
+            if t["event"].query():
+                self._resolve(t)
             else:
-                keep.append((host, ev, cap))
+                keep.append(t)
         self.pending = keep
+
+    def check(self, ticket) -> None:
+        """Called by the view's own backward: waits for ITS count (recorded right after bin_scan, long passed by the
+        time the loss has been enqueued) and raises if the view was truncated."""
+        ticket["checked"] = True
+        ticket["event"].synchronize()
+        self._resolve(ticket)
+        if self.unreported is not None and self.unreported == (ticket["count"], ticket["cap"]):
+            self.unreported = None
+        if ticket["count"] > ticket["cap"]:
+            raise DnrCapacityError(
+                f"this view needs {ticket['count']} intersection slots but was rendered with {ticket['cap']}: outputs and "
+                "gradients are truncated.  The capacity has been raised — run the view again (or use sync_free=False).")
+
+    def raise_unreported(self) -> None:
+        if self.unreported is not None:
+            need, cap = self.unreported
+            self.unreported = None
+            raise DnrCapacityError(
+                f"an earlier no-grad view needed {need} intersection slots but was rendered with {cap}: that render was "
+                "truncated.  The capacity has been raised — render it again.")
 
 
 _CAPACITY: dict = {}
 
 
 def suggested_capacity(n_gauss: int, width: int, height: int, render_normals: bool = True, exact_lists: bool = False,
-                       device_index: Optional[int] = None) -> int:
-    """Capacity (1.15 x the largest intersection count seen in sync-free mode, 2M-rounded) for graph capture."""
+                       device_index: Optional[int] = None, list_shift: Optional[int] = None) -> int:
+    """Capacity (1.15 x the largest intersection count seen in sync-free mode, rounded up) for graph capture."""
     best = 0
-    for (di, n, w, h, rn, ex), t in _CAPACITY.items():
-        if (n, w, h, rn, ex) == (n_gauss, width, height, render_normals, exact_lists) and (device_index in (None, di)):
+    for (di, n, w, h, rn, ex, lt), t in _CAPACITY.items():
+        if (n, w, h, rn, ex) == (n_gauss, width, height, render_normals, exact_lists) and (device_index in (None, di)) \
+                and (list_shift is None or lt == TILE << list_shift):
             t.drain(wait=True)
             best = max(best, t.capacity())
     return best
@@ -128,7 +166,10 @@ class RasterSettings:
     exact_lists: bool = False  # parity mode: gsplat's full bbox intersection lists instead of the precise-hit lists
     sync_free: bool = False  # size the intersection buffers from past views instead of reading the count back
     fixed_capacity: int = 0  # > 0: use exactly this many intersection slots, no host bookkeeping (CUDA-graph capture)
-    compact_bwd: bool = False  # EXPERIMENTAL (not GPU-validated yet): project_bwd over visible Gaussians only
+    compact_bwd: bool = False  # project_bwd walks the depth-sorted index (validated in round 2: slower; kept for A/B)
+    list_shift: int = 2  # intersection lists per (16 << list_shift)-pixel supertile; forced to 0 by exact_lists
+    touched_bwd: bool = True  # project_bwd only over the Gaussians that received a raster gradient
+    variant: int = 0  # kernel tuning knob (csrc/raster.cu): bit 0 butterfly reduction, bit 1 scalar arithmetic
 
 
 class RasterOutput(NamedTuple):
@@ -184,6 +225,8 @@ def _base_args(s: RasterSettings, n: int, sh_bases: int, accumulate: bool = Fals
     if s.exact_lists:
         flags |= L.FLAG_EXACT_LISTS
     a.flags = flags
+    a.list_shift = 0 if s.exact_lists else int(s.list_shift)
+    a.variant = int(s.variant)
     a.near_plane, a.far_plane, a.eps2d, a.radius_clip = s.near_plane, s.far_plane, s.eps2d, 0.0
     a.background[0], a.background[1], a.background[2] = s.background
     return a
@@ -235,10 +278,13 @@ class _DnRasterize(torch.autograd.Function):
             c2w = None if host_cam is not None else c2w.contiguous().float().view(3, 4)
         H, W = s.height, s.width
         tiles_x, tiles_y = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
-        n_tiles = tiles_x * tiles_y
+        list_tile = TILE << (0 if s.exact_lists else int(s.list_shift))  # one sorted list per list_tile^2 pixels
+        lists_x, lists_y = (W + list_tile - 1) // list_tile, (H + list_tile - 1) // list_tile
+        n_tiles = lists_x * lists_y
         rec_f = L.REC_FLOATS_N if s.render_normals else L.REC_FLOATS
         st = _stream()
         ctx.fwd_stream = torch.cuda.current_stream()
+        ctx.capacity_ticket = None
 
         radii = torch.empty(n, **i32)
         means2d = torch.empty(n, 2, **f32)
@@ -265,17 +311,19 @@ class _DnRasterize(torch.autograd.Function):
 
         ws_scan = torch.empty(lib.dnr_bin_scan_workspace_bytes(n), dtype=torch.uint8, device=dev)
         _set(a, ws_scan=ws_scan)
-        cap_key = (dev.index, n, W, H, s.render_normals, s.exact_lists)
+        cap_key = (dev.index, n, W, H, s.render_normals, s.exact_lists, list_tile)
         tracker = _CAPACITY.get(cap_key) if s.sync_free else None
         if s.fixed_capacity > 0:
-            # graph-capturable: no read-back, no events, no host state; a view needing more slots is truncated
+            # graph-capturable: no read-back, no events, no host state; the owner of the graph (graph_step.py) watches
+            # info["n_isects_dev"] and raises DnrCapacityError when a replay needed more slots
             L.check(_timed("bin_scan", lib.dnr_bin_scan, C.byref(a), st, None), "dnr_bin_scan")
             n_isects = int(s.fixed_capacity)
         elif tracker is not None and tracker.ready():
             # sync-free: nothing is read back on this stream; capacity comes from the counts of earlier views
+            tracker.raise_unreported()
             L.check(_timed("bin_scan", lib.dnr_bin_scan, C.byref(a), st, None), "dnr_bin_scan")
             n_isects = tracker.capacity()
-            tracker.observe(n_isects_dev, n_isects)
+            ctx.capacity_ticket = (tracker, tracker.observe(n_isects_dev, n_isects))
         else:
             total = C.c_int64(0)
             L.check(_timed("bin_scan", lib.dnr_bin_scan, C.byref(a), st, C.byref(total)), "dnr_bin_scan")
@@ -304,9 +352,10 @@ class _DnRasterize(torch.autograd.Function):
         last_ids = torch.empty(H, W, **i32)
         clamp_mask = torch.empty(H, W, dtype=torch.uint8, device=dev)
         depth_max = torch.empty(1, **i32)
+        stats = holder.get("stats")  # optional uint64[4] device counters (list entries walked / kept by the tile filter)
         _set(a, out_rgb=out_rgb, out_depth=out_depth, out_alpha=out_alpha, out_normal=out_normal,
              out_surface_normal=out_sn, last_ids=last_ids, normal_norm=normal_norm, clamp_mask=clamp_mask,
-             depth_max=depth_max)
+             depth_max=depth_max, stats=stats)
         L.check(_timed("raster_fwd", lib.dnr_raster_fwd, C.byref(a), st), "dnr_raster_fwd")
         L.check(_timed("finalize_fwd", lib.dnr_finalize_fwd, C.byref(a), st), "dnr_finalize_fwd")
 
@@ -314,15 +363,16 @@ class _DnRasterize(torch.autograd.Function):
         ctx.save_for_backward(means, quats, scales, opac, sh_dc, sh_rest, viewmat, K, c2w if s.render_normals else None)
         ctx.ws_scan = ws_scan if s.compact_bwd else None
         ctx.state = dict(radii=radii, records=records, flatten_ids=flatten_ids, tile_offsets=tile_offsets,
-                         out_depth=out_depth, out_alpha=out_alpha, out_normal=out_normal, last_ids=last_ids,
+                         out_rgb=out_rgb, out_depth=out_depth, out_alpha=out_alpha, out_normal=out_normal, last_ids=last_ids,
                          normal_norm=normal_norm, clamp_mask=clamp_mask, means2d=means2d)
+        ctx.holder = holder
         ctx.opac_shape = opacities.shape
         normal_ret = out_normal if s.render_normals else torch.zeros(H, W, 3, **f32)
         sn_ret = out_sn if s.surface_normal else torch.zeros(H, W, 3, **f32)
         info = dict(flatten_ids=flatten_ids[:n_isects], tile_offsets=tile_offsets, last_ids=last_ids, n_isects=n_isects,
                     n_isects_dev=n_isects_dev,
                     colors=colors, opacities=opac_act, compensations=comp, tile_width=tiles_x, tile_height=tiles_y,
-                    depth_max=depth_max)
+                    list_tile=list_tile, lists_x=lists_x, lists_y=lists_y, depth_max=depth_max)
         ctx.grad_sink = holder.pop("grad_sink", None)
         holder.update(info)
         ctx.mark_non_differentiable(sn_ret, means2d, radii, depths, conics, tiles_per_gauss, normals_world)
@@ -340,6 +390,9 @@ class _DnRasterize(torch.autograd.Function):
     def _backward(ctx, v_rgb, v_depth, v_normal, v_alpha):
         lib = L.load()
         s: RasterSettings = ctx.settings
+        if ctx.capacity_ticket is not None:  # sync-free sizing: never produce gradients from a truncated render
+            tracker, ticket = ctx.capacity_ticket
+            tracker.check(ticket)
         means, quats, scales, opac, sh_dc, sh_rest, viewmat, K, c2w = ctx.saved_tensors
         S = ctx.state
         n, dev = ctx.n, means.device
@@ -347,7 +400,10 @@ class _DnRasterize(torch.autograd.Function):
         st = _stream()
 
         def prep(g):
-            return None if g is None else g.contiguous().float()
+            # zero-stride tokens stand for "this gradient is evaluated inside dnr_raster_bwd" (deferred losses, below)
+            if g is None or _is_zero_token(g):
+                return None
+            return g.contiguous().float()
 
         v_rgb, v_depth, v_alpha = prep(v_rgb), prep(v_depth), prep(v_alpha)
         v_normal = prep(v_normal) if s.render_normals else None
@@ -357,23 +413,33 @@ class _DnRasterize(torch.autograd.Function):
         a.n_isects = ctx.n_isects
         _set(a, viewmat=viewmat, K=K, c2w=c2w, means=means, quats=quats, scales=scales, opacities=opac, sh_dc=sh_dc,
              sh_rest=sh_rest if ctx.sh_bases > 1 else None, radii=S["radii"], records=S["records"],
-             flatten_ids=S["flatten_ids"], tile_offsets=S["tile_offsets"], out_depth=S["out_depth"],
+             flatten_ids=S["flatten_ids"], tile_offsets=S["tile_offsets"], out_rgb=S["out_rgb"], out_depth=S["out_depth"],
              out_alpha=S["out_alpha"], out_normal=S["out_normal"], last_ids=S["last_ids"],
              normal_norm=S["normal_norm"], clamp_mask=S["clamp_mask"], v_rgb=v_rgb, v_depth=v_depth,
-             v_normal=v_normal, v_alpha=v_alpha, grad_records=grad_records)
+             v_normal=v_normal, v_alpha=v_alpha, grad_records=grad_records, stats=ctx.holder.get("stats"))
+        # losses whose backward asked to be evaluated in the raster kernel's prologue (regularization_strategy.py)
+        keep = _apply_deferred_losses(a, ctx.holder.pop("deferred", None))
+        touched = None
+        if s.touched_bwd and not s.compact_bwd:
+            touched = torch.empty(n, dtype=torch.uint8, device=dev)
+            _set(a, touched=touched)
         L.check(_timed("raster_bwd", lib.dnr_raster_bwd, C.byref(a), st), "dnr_raster_bwd")
+        del keep
         sink = ctx.grad_sink
         if s.compact_bwd:
             a.flags |= L.FLAG_COMPACT_BWD
             a.depth_order = lib.dnr_depth_order_ptr(ctx.ws_scan.data_ptr(), n)
+        scattered = s.compact_bwd or touched is not None  # accumulate-only kernels: buffers must be pre-zeroed
+        if touched is not None:
+            a.flags |= L.FLAG_TOUCHED_BWD
         if sink is not None:
             # write straight into the caller's (pre-zeroed, e.g. flat all-reduce bucket) gradient buffers
             a.flags |= L.FLAG_ACCUMULATE
             v_means, v_quats, v_scales = sink["means"], sink["quats"], sink["scales"]
             v_opac, v_sh_dc, v_sh_rest = sink["opacities"], sink["features_dc"], sink["features_rest"]
         else:
-            alloc = torch.zeros_like if s.compact_bwd else torch.empty_like  # the compact kernel only accumulates
-            if s.compact_bwd:
+            alloc = torch.zeros_like if scattered else torch.empty_like
+            if scattered:
                 a.flags |= L.FLAG_ACCUMULATE
             v_means = alloc(means)
             v_quats = alloc(quats)
@@ -381,8 +447,8 @@ class _DnRasterize(torch.autograd.Function):
             v_opac = alloc(opac)
             v_sh_dc = alloc(sh_dc)
             v_sh_rest = alloc(sh_rest)
-        v_m2d = torch.empty(n, 2, **f32)
-        v_m2d_abs = torch.empty(n, 2, **f32)
+        v_m2d = (torch.zeros if touched is not None else torch.empty)(n, 2, **f32)
+        v_m2d_abs = (torch.zeros if touched is not None else torch.empty)(n, 2, **f32)
         _set(a, v_means=v_means, v_quats=v_quats, v_scales=v_scales, v_opacities=v_opac, v_sh_dc=v_sh_dc,
              v_sh_rest=v_sh_rest if ctx.sh_bases > 1 else None, v_means2d=v_m2d, v_means2d_abs=v_m2d_abs)
         L.check(_timed("project_bwd", lib.dnr_project_bwd, C.byref(a), st), "dnr_project_bwd")
@@ -394,6 +460,67 @@ class _DnRasterize(torch.autograd.Function):
         return (v_means, v_quats, v_scales, v_opac.view(ctx.opac_shape), v_sh_dc, v_sh_rest, None, None, None, None, None)
 
 
+def _apply_deferred_losses(a: L.DnrArgs, deferred: Optional[dict]):
+    """Fills the DNR_LOSS_FUSED_BWD fields of `a` from the specs the loss Functions left in the raster holder; returns
+    the tensors that must stay alive until the launch."""
+    if not deferred:
+        return None
+    keep = []
+    flags = L.LOSS_FUSED_BWD
+    l1 = deferred.get("l1")
+    if l1 is not None:
+        gt, v = l1["gt"], l1["v"]
+        if gt.dtype == torch.uint8:
+            flags |= L.LOSS_IMG_U8
+        a.gt_image, a.v_l1 = gt.data_ptr(), v.data_ptr()
+        keep += [gt, v]
+    reg = deferred.get("reg")
+    if reg is not None:
+        a.depth_loss_type, a.use_normal_loss = reg["depth_type"], reg["use_normal"]
+        a.depth_lambda, a.depth_tolerance = reg["depth_lambda"], reg["depth_tolerance"]
+        for k in ("gt_depth", "gt_normal", "gt_rgb", "loss_partials"):
+            t = reg.get(k)
+            setattr(a, k, None if t is None else t.data_ptr())
+            keep.append(t)
+        a.v_loss = reg["v"].data_ptr()
+        keep.append(reg["v"])
+        if reg.get("gt_normal") is not None and reg["gt_normal"].dtype == torch.uint8:
+            flags |= L.LOSS_NORMAL_U8
+        if reg.get("edge_image") is not None:  # EdgeAwareLogL1 weights straight from the uint8 image
+            img = reg["edge_image"]
+            if l1 is not None and l1["gt"].data_ptr() != img.data_ptr():
+                raise L.DnrError("fused losses: the photometric target and the edge image must be the same uint8 tensor")
+            a.gt_image = img.data_ptr()
+            flags |= L.LOSS_EDGE_FROM_IMAGE | L.LOSS_IMG_U8
+            keep.append(img)
+    a.loss_flags = flags
+    return keep
+
+
+def raster_holder(t: Tensor) -> Optional[dict]:
+    """The holder dict of the dn_rasterize call that produced `t` (a RasterOutput map), or None.  Loss Functions use it
+    to hand their backward to dnr_raster_bwd: they store a spec under holder["deferred"] and return zero_token(...)."""
+    return getattr(t, "_dnr_holder", None)
+
+
+def zero_token(like: Tensor) -> Tensor:
+    """A zero gradient without memory: zero-stride view of a cached scalar 0 (adds exactly nothing if autograd sums it
+    with a real gradient; recognised and skipped by _DnRasterize.backward)."""
+    z = _ZERO.get(like.device)
+    if z is None:
+        z = _ZERO[like.device] = torch.zeros((), dtype=torch.float32, device=like.device)
+    return z.expand(like.shape)
+
+
+_ZERO: dict = {}
+
+
+def _is_zero_token(g: Tensor) -> bool:
+    # identity, not just shape: `x.sum().backward()` also yields zero-stride gradients (of ones)
+    z = _ZERO.get(g.device)
+    return z is not None and g.data_ptr() == z.data_ptr() and all(sd == 0 for sd in g.stride())
+
+
 def dn_rasterize(
     means: Tensor, quats: Tensor, scales: Tensor, opacities: Tensor, sh_dc: Tensor, sh_rest: Tensor,
     viewmat: Tensor, K: Tensor, width: int, height: int, *, sh_degree: int = 3, near_plane: float = 0.01,
@@ -401,6 +528,7 @@ def dn_rasterize(
     background: Sequence[float] = (0.0, 0.0, 0.0), render_normals: bool = True, c2w: Optional[Tensor] = None,
     activated: bool = False, surface_normal: bool = True, grad_sink: Optional[dict] = None,
     exact_lists: bool = False, sync_free: bool = False, fixed_capacity: int = 0, compact_bwd: bool = False,
+    list_shift: int = 2, touched_bwd: bool = True, variant: int = 0, stats: Optional[Tensor] = None,
 ) -> RasterOutput:
     """Renders one view.  Inputs are the reference's RAW gauss_params (log-scales, opacity logits,
     un-normalised wxyz quats, SH coefficients split as features_dc / features_rest) unless
@@ -412,13 +540,19 @@ def dn_rasterize(
     settings = RasterSettings(width=int(width), height=int(height), sh_degree=int(sh_degree), near_plane=near_plane,
                               far_plane=far_plane, eps2d=eps2d, antialiased=antialiased, render_normals=render_normals,
                               activated=activated, background=bg, surface_normal=surface_normal, exact_lists=exact_lists,
-                              sync_free=sync_free, fixed_capacity=int(fixed_capacity), compact_bwd=compact_bwd)
+                              sync_free=sync_free, fixed_capacity=int(fixed_capacity), compact_bwd=compact_bwd,
+                              list_shift=int(list_shift), touched_bwd=touched_bwd, variant=int(variant))
     info: dict = {}
+    if stats is not None:
+        info["stats"] = stats
     if grad_sink is not None:
         # dict with fp32 contiguous buffers shaped like the six parameters (keys: means, quats, scales, opacities,
         # features_dc, features_rest); the backward ACCUMULATES into them and autograd sees no gradient.
         info["grad_sink"] = grad_sink
     outs = _DnRasterize.apply(means, quats, scales, opacities, sh_dc, sh_rest, viewmat, K, c2w, settings, info)
+    if torch.is_grad_enabled():
+        for t in outs[:4]:  # rgb, depth, normal, alpha: losses may defer their backward to dnr_raster_bwd through this
+            t._dnr_holder = info
     return RasterOutput(*outs, info)
 
 

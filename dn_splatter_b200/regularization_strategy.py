@@ -30,12 +30,28 @@ def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _shared_holder(*tensors):
+    """The dn_rasterize holder shared by all the given rendered maps (None if any map is not a direct raster output or
+    they come from different renders): only then can a loss hand its backward to dnr_raster_bwd."""
+    from .rasterize import raster_holder
+
+    hs = [raster_holder(t) for t in tensors if t is not None]
+    if not hs or any(h is None for h in hs) or any(h is not hs[0] for h in hs):
+        return None
+    return hs[0]
+
+
 class _FusedDNLoss(torch.autograd.Function):
-    """(1+lambda) * depth_term + L1(normal) + TV(normal) on rendered maps; see include/dnr.h dnr_loss_*."""
+    """(1+lambda) * depth_term + L1(normal) + TV(normal) on rendered maps; see include/dnr.h dnr_loss_*.
+
+    `gt_normal` may be uint8 (value / 255, as get_gt_img does) and `edge_image` the uint8 photometric image (clamped
+    below at 10/255 in the kernel, dn_model.py:633) instead of the fp32 `gt_img`.  With a raster `holder` the backward
+    does not write gradient images: it leaves a spec for dnr_raster_bwd, whose prologue evaluates the same formulas
+    per pixel (BASELINE north_star: the regularisers are fused into the backward kernel)."""
 
     @staticmethod
     def forward(ctx, pred_depth, pred_normal, gt_depth, gt_normal, gt_img, depth_type: int, depth_lambda: float,
-                depth_tolerance: float, use_normal: bool):
+                depth_tolerance: float, use_normal: bool, holder=None, edge_image=None):
         lib = L.load()
         ref = pred_depth if pred_depth is not None else pred_normal
         if ref.device.type != "cuda":
@@ -46,22 +62,37 @@ class _FusedDNLoss(torch.autograd.Function):
             H, W = pred_normal.shape[0], pred_normal.shape[1]
         dev = ref.device
 
-        def prep(t):
-            return None if t is None else t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        def prep(t, keep_u8=False):
+            if t is None:
+                return None
+            if keep_u8 and t.dtype == torch.uint8:
+                return t.detach().to(device=dev).contiguous()
+            return t.detach().to(device=dev, dtype=torch.float32).contiguous()
 
-        pd, pn, gd, gn, gi = prep(pred_depth), prep(pred_normal), prep(gt_depth), prep(gt_normal), prep(gt_img)
+        pd, pn, gd, gi = prep(pred_depth), prep(pred_normal), prep(gt_depth), prep(gt_img)
+        gn = prep(gt_normal, keep_u8=True)
+        ei = prep(edge_image, keep_u8=True)
+        flags = 0
+        if gn is not None and gn.dtype == torch.uint8:
+            flags |= L.LOSS_NORMAL_U8
+        if ei is not None:
+            assert ei.dtype == torch.uint8, "edge_image is the raw uint8 image"
+            flags |= L.LOSS_EDGE_FROM_IMAGE | L.LOSS_IMG_U8
         partials = torch.empty(12, dtype=torch.float32, device=dev)
         a = L.DnrArgs()
         a.width, a.height = W, H
         a.depth_loss_type, a.use_normal_loss = int(depth_type), int(bool(use_normal))
         a.depth_lambda, a.depth_tolerance = float(depth_lambda), float(depth_tolerance)
-        for k, t in dict(out_depth=pd, out_normal=pn, gt_depth=gd, gt_normal=gn, gt_rgb=gi, loss_partials=partials).items():
+        a.loss_flags = flags
+        for k, t in dict(out_depth=pd, out_normal=pn, gt_depth=gd, gt_normal=gn, gt_rgb=gi, gt_image=ei,
+                         loss_partials=partials).items():
             setattr(a, k, None if t is None else t.data_ptr())
         L.check(lib.dnr_loss_fwd(C.byref(a), _stream()), "dnr_loss_fwd")
-        ctx.keep = (pd, pn, gd, gn, gi, partials)
+        ctx.keep = (pd, pn, gd, gn, gi, ei, partials)
         ctx.fwd_stream = torch.cuda.current_stream()
-        ctx.cfg = (W, H, int(depth_type), int(bool(use_normal)), float(depth_lambda), float(depth_tolerance))
+        ctx.cfg = (W, H, int(depth_type), int(bool(use_normal)), float(depth_lambda), float(depth_tolerance), flags)
         ctx.shapes = (None if pred_depth is None else pred_depth.shape, None if pred_normal is None else pred_normal.shape)
+        ctx.holder = holder
         return partials[11].clone()
 
     @staticmethod
@@ -72,21 +103,32 @@ class _FusedDNLoss(torch.autograd.Function):
     @staticmethod
     def _backward(ctx, v):
         lib = L.load()
-        pd, pn, gd, gn, gi, partials = ctx.keep
-        W, H, depth_type, use_normal, lam, tol = ctx.cfg
+        pd, pn, gd, gn, gi, ei, partials = ctx.keep
+        W, H, depth_type, use_normal, lam, tol, flags = ctx.cfg
         v = v.detach().to(torch.float32).contiguous()
+        none9 = (None,) * 9
+        if ctx.holder is not None:
+            from .rasterize import zero_token
+
+            ctx.holder.setdefault("deferred", {})["reg"] = dict(
+                depth_type=depth_type, use_normal=use_normal, depth_lambda=lam, depth_tolerance=tol, gt_depth=gd,
+                gt_normal=gn if use_normal else None, gt_rgb=gi, edge_image=ei, loss_partials=partials, v=v)
+            vd = zero_token(pd.view(ctx.shapes[0])) if (depth_type and ctx.needs_input_grad[0]) else None
+            vn = zero_token(pn.view(ctx.shapes[1])) if (use_normal and ctx.needs_input_grad[1]) else None
+            return (vd, vn) + none9
         a = L.DnrArgs()
         a.width, a.height = W, H
         a.depth_loss_type, a.use_normal_loss, a.depth_lambda, a.depth_tolerance = depth_type, use_normal, lam, tol
-        for k, t in dict(out_depth=pd, out_normal=pn, gt_depth=gd, gt_normal=gn, gt_rgb=gi, loss_partials=partials,
-                         v_loss=v).items():
+        a.loss_flags = flags
+        for k, t in dict(out_depth=pd, out_normal=pn, gt_depth=gd, gt_normal=gn, gt_rgb=gi, gt_image=ei,
+                         loss_partials=partials, v_loss=v).items():
             setattr(a, k, None if t is None else t.data_ptr())
         vd = torch.empty(ctx.shapes[0], dtype=torch.float32, device=v.device) if (depth_type and ctx.needs_input_grad[0]) else None
         vn = torch.empty(ctx.shapes[1], dtype=torch.float32, device=v.device) if (use_normal and ctx.needs_input_grad[1]) else None
         if vd is not None or vn is not None:
             L.check(lib.dnr_loss_bwd(C.byref(a), None if vd is None else vd.data_ptr(),
                                      None if vn is None else vn.data_ptr(), _stream()), "dnr_loss_bwd")
-        return vd, vn, None, None, None, None, None, None, None
+        return (vd, vn) + none9
 
 
 class _ScaleLoss(torch.autograd.Function):
@@ -121,10 +163,11 @@ class _ScaleLoss(torch.autograd.Function):
 
 
 class FusedL1(torch.autograd.Function):
-    """mean |pred - gt| with gt fp32 or uint8 (/255): the parent SplatfactoModel's photometric L1 in one pass each way."""
+    """mean |pred - gt| with gt fp32 or uint8 (/255): the parent SplatfactoModel's photometric L1 in one pass each way.
+    With a raster `holder` (pred is a direct dn_rasterize output) the backward is evaluated inside dnr_raster_bwd."""
 
     @staticmethod
-    def forward(ctx, pred, gt):
+    def forward(ctx, pred, gt, holder=None):
         lib = L.load()
         if pred.device.type != "cuda" or gt.device != pred.device:
             raise L.DnrError("FusedL1 needs CUDA tensors on one device (no CPU path)")
@@ -139,6 +182,7 @@ class FusedL1(torch.autograd.Function):
         ctx.keep = (p, g)
         ctx.shape = pred.shape
         ctx.fwd_stream = torch.cuda.current_stream()
+        ctx.holder = holder
         return out[0].clone()
 
     @staticmethod
@@ -151,10 +195,15 @@ class FusedL1(torch.autograd.Function):
         lib = L.load()
         p, g = ctx.keep
         v = v.detach().float().contiguous()
+        if ctx.holder is not None:
+            from .rasterize import zero_token
+
+            ctx.holder.setdefault("deferred", {})["l1"] = dict(gt=g, v=v)
+            return zero_token(p.view(ctx.shape)), None, None
         vp = torch.empty_like(p)
         L.check(lib.dnr_l1_bwd(p.data_ptr(), g.data_ptr(), p.numel(), int(g.dtype == torch.uint8), v.data_ptr(), vp.data_ptr(),
                                _stream()), "dnr_l1_bwd")
-        return vp.view(ctx.shape), None
+        return vp.view(ctx.shape), None, None
 
 
 class FusedSSIM(torch.autograd.Function):
@@ -243,6 +292,9 @@ class DNRegularization(RegularizationStrategy):
     def _fusable(self, with_depth: bool) -> bool:
         return (not with_depth) or self.depth_loss_type in _FUSED_DEPTH
 
+    fuse_backward = True
+    """Hand the backward of the fused terms to dnr_raster_bwd when the maps are direct raster outputs."""
+
     def get_loss(self, pred_depth, gt_depth, pred_normal, gt_normal, **kwargs):
         with_depth = self.depth_loss is not None
         with_normal = self.normal_loss is not None
@@ -251,12 +303,21 @@ class DNRegularization(RegularizationStrategy):
                 raise TypeError("use_depth_loss is set but the batch holds no depth (reference: '>' on NoneType)")
             dtype = _FUSED_DEPTH[self.depth_loss_type] if with_depth else 0
             gt_img = kwargs.get("gt_img") if dtype == 1 else None
+            edge_image = None
             if dtype == 1 and gt_img is None:
                 raise KeyError("gt_img")
-            loss = _FusedDNLoss.apply(pred_depth if with_depth else None, pred_normal if with_normal else None,
-                                      gt_depth if with_depth else None, gt_normal if with_normal else None, gt_img,
-                                      dtype, self.depth_lambda, self.depth_tolerance, with_normal)
+            if gt_img is not None and gt_img.dtype == torch.uint8:  # raw image: clamped (10/255) inside the kernels
+                gt_img, edge_image = None, gt_img
+            pd, pn = (pred_depth if with_depth else None), (pred_normal if with_normal else None)
+            holder = _shared_holder(pd, pn) if self.fuse_backward else None
+            loss = _FusedDNLoss.apply(pd, pn, gt_depth if with_depth else None, gt_normal if with_normal else None, gt_img,
+                                      dtype, self.depth_lambda, self.depth_tolerance, with_normal, holder, edge_image)
         else:
+            if gt_normal is not None and gt_normal.dtype == torch.uint8:
+                gt_normal = u8_to_float(gt_normal) if gt_normal.is_cuda else gt_normal.float() / 255.0
+            if kwargs.get("gt_img") is not None and kwargs["gt_img"].dtype == torch.uint8:
+                gi = kwargs["gt_img"]
+                kwargs["gt_img"] = u8_to_float(gi, 255.0, 10 / 255.0) if gi.is_cuda else (gi.float() / 255.0).clamp(min=10 / 255.0)
             loss = 0.0
             if with_depth:
                 loss = loss + self.get_depth_loss(pred_depth, gt_depth, **kwargs)

@@ -58,7 +58,9 @@ class Trainer:
         info: Optional[Dict[str, int]] = None
         if step > 0 and step % m.config.refine_every == 0:
             st = m.__dict__.get("_densify_state")
-            if self.world_size > 1 and st is not None:
+            # Reduce ONLY when refinement_after will consume (and reset) the statistics: during warm-up it returns without
+            # resetting them, and an in-place all-reduce there would be summed again at the next boundary (weight W^k).
+            if self.world_size > 1 and st is not None and step > m.config.warmup_length:
                 st.all_reduce_()  # identical statistics -> identical decisions (and identical split samples: same seed)
             info = m.refinement_after(self.optimizers, step, generator=self.generator)
         self.step += 1

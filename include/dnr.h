@@ -53,6 +53,7 @@ extern "C" {
                                     (a->depth_order), so only visible Gaussians occupy lanes; needs DNR_FLAG_ACCUMULATE */
 #define DNR_FLAG_HOST_CAMERA 32u /* camera passed by value in host_cam[] (no device reads, no H2D copy) */
 #define DNR_FLAG_EXACT_LISTS 16u /* parity mode: emit gsplat's full bbox intersection lists (no precise-hit cull) */
+#define DNR_FLAG_TOUCHED_BWD 128u /* project_bwd processes only Gaussians with touched[g] != 0 (needs DNR_FLAG_ACCUMULATE) */
 
 /* floats per packed per-Gaussian raster record, without / with normals */
 #define DNR_REC_FLOATS 12
@@ -68,7 +69,9 @@ typedef struct DnrArgs {
   int32_t sh_degree; /* active degree 0..3 (dn_model.py:487-490) */
   int32_t sh_bases;  /* bases stored per Gaussian: sh_rest is [N, sh_bases-1, 3] */
   uint32_t flags;    /* DNR_FLAG_* */
-  int32_t reserved0;
+  int32_t list_shift; /* intersection lists are kept per SUPERTILE of (16 << list_shift)^2 pixels (0..3); every 16x16 tile
+                         walks its supertile's list and drops, inside the raster kernels, the entries that cannot reach it.
+                         0 = one list per tile (required with DNR_FLAG_EXACT_LISTS: gsplat's lists) */
   float near_plane, far_plane, eps2d, radius_clip;
   float background[3];
   float reserved1;
@@ -150,7 +153,29 @@ typedef struct DnrArgs {
   /* with DNR_FLAG_HOST_CAMERA: [0..15] viewmat, [16..19] fx fy cx cy, [20..31] c2w[3,4]; viewmat/K/c2w pointers unused */
   float host_cam[32];
   const int32_t* depth_order; /* [N] Gaussian ids sorted by depth, visible first (dnr_depth_order_ptr); COMPACT_BWD only */
+
+  /* ---- loss gradients evaluated inside dnr_raster_bwd (BASELINE north_star: regularisers fused into the backward) ----
+   * With DNR_LOSS_FUSED_BWD the per-pixel gradients of
+   *   *v_l1  * mean|rgb - gt_image|                     (parent photometric L1; term off when v_l1 == NULL)
+   *   *v_loss * DNRegularization(depth, normal)         (dnr_loss_fwd's terms; uses gt_depth, gt_normal, gt_rgb /
+   *                                                      gt_image, loss_partials, depth_* fields, use_normal_loss)
+   * are computed in the kernel's prologue from the rendered maps instead of being read from v_rgb / v_depth / v_normal
+   * images; non-NULL v_rgb / v_depth / v_normal / v_alpha are ADDED (e.g. the SSIM gradient). */
+  uint32_t loss_flags;   /* DNR_LOSS_* */
+  int32_t variant;       /* kernel tuning knob (0 = default); see csrc/raster.cu */
+  const void* gt_image;  /* [H,W,3] photometric target: uint8 (DNR_LOSS_IMG_U8, scaled by 1/255) or fp32 */
+  const float* v_l1;     /* [1] device scalar */
+  uint8_t* touched;      /* [N] or NULL: dnr_raster_bwd sets touched[g] = 1 for every Gaussian that received a gradient
+                            (zeroed by the call); dnr_project_bwd then skips the others (DNR_FLAG_TOUCHED_BWD) */
+  uint64_t* stats; /* [4] or NULL: += {list entries walked, entries kept by the tile filter} (fwd: [0],[1]; bwd: [2],[3]) */
 } DnrArgs;
+
+/* loss_flags */
+#define DNR_LOSS_FUSED_BWD 1u  /* dnr_raster_bwd evaluates the loss gradients itself (see above) */
+#define DNR_LOSS_IMG_U8 2u     /* gt_image is uint8 */
+#define DNR_LOSS_NORMAL_U8 4u  /* gt_normal is uint8 [H,W,3] (value / 255, as get_gt_img does) */
+#define DNR_LOSS_EDGE_FROM_IMAGE 8u /* EdgeAwareLogL1 edge weights from gt_image clamped below at 10/255 (dn_model.py:633)
+                                       instead of the fp32 gt_rgb map */
 
 int dnr_version(void);
 const char* dnr_error_string(int code);

@@ -15,7 +15,7 @@ class _Out:
 def oracle_rasterize(means, quats, scales, opacities, sh_dc, sh_rest, viewmat, K, width, height, *, sh_degree=3,
                      near_plane=0.01, far_plane=1e10, eps2d=0.3, antialiased=False, background=(0, 0, 0), render_normals=True,
                      c2w=None, activated=False, surface_normal=True, grad_sink=None, exact_lists=False, sync_free=False,
-                     fixed_capacity=0):
+                     fixed_capacity=0, **_kernel_options):
     if isinstance(background, torch.Tensor):
         background = background.tolist()
     bg = torch.tensor(list(background), dtype=torch.float32)
@@ -60,7 +60,7 @@ def cpu_proxy():
 
     class L1Proxy:
         @staticmethod
-        def apply(pred, gt):
+        def apply(pred, gt, holder=None):
             g = gt.float() / 255.0 if gt.dtype == torch.uint8 else gt
             return (pred - g).abs().mean()
 
@@ -71,8 +71,12 @@ def cpu_proxy():
 
     class DNProxy:
         @staticmethod
-        def apply(pd, pn, gd, gn, gi, dtype, lam, tol, use_normal):
+        def apply(pd, pn, gd, gn, gi, dtype, lam, tol, use_normal, holder=None, edge_image=None):
             types = {0: None, 1: "EdgeAwareLogL1", 2: "LogL1", 3: "L1", 4: "MSE"}
+            if edge_image is not None:
+                gi = (edge_image.float() / 255.0).clamp(min=10 / 255.0)
+            if gn is not None and gn.dtype == torch.uint8:
+                gn = gn.float() / 255.0
             full = dn_ref.dn_regularization(pd if pd is not None else torch.zeros(1, 1, 1), gd, pn, gn, torch.zeros(1, 3),
                                             gi, depth_lambda=lam, depth_tolerance=tol, depth_loss_type=types[dtype],
                                             use_normal_loss=bool(use_normal))

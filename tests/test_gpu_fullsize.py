@@ -52,9 +52,10 @@ def test_fullsize_lists_and_images(scene):
         assert bool((out.radii[ids] > 0).all())
         # last_ids of covered pixels point inside their own tile's slice
         last = out.info["last_ids"].long()
-        ty = torch.arange(H, device=last.device)[:, None] // 16
-        tx = torch.arange(W, device=last.device)[None, :] // 16
-        t = ty * out.info["tile_width"] + tx
+        lt = out.info["list_tile"]  # 16 for the exact lists, 16 << list_shift (supertile lists) otherwise
+        ty = torch.arange(H, device=last.device)[:, None] // lt
+        tx = torch.arange(W, device=last.device)[None, :] // lt
+        t = ty * out.info["lists_x"] + tx
         cov = out.alpha[..., 0] > 0
         assert bool(((last >= offs[t]) & (last < offs[t + 1]))[cov].all())
     assert float(cut.alpha.min()) >= 0.0 and float(cut.alpha.max()) < 1.0

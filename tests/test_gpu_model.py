@@ -269,3 +269,42 @@ def test_fused_adam_matches_torch_adam():
         for x, y in ((fused.state[a[k]]["exp_avg"], ref[k].state[b[k]]["exp_avg"]),
                      (fused.state[a[k]]["exp_avg_sq"], ref[k].state[b[k]]["exp_avg_sq"]), (a[k].data, b[k].data)):
             assert float((x - y).abs().max()) <= 1e-5 * float(y.abs().max()), k
+
+
+@needs_cuda
+@pytest.mark.parametrize("depth_type,ssim_lambda", [("EdgeAwareLogL1", 0.0), ("EdgeAwareLogL1", 0.2), ("LogL1", 0.0),
+                                                     ("L1", 0.2), ("mse", 0.0)])
+def test_loss_gradients_fused_into_raster_bwd_match_the_gradient_image_path(depth_type, ssim_lambda):
+    """BASELINE north_star: the Depth / Normal / TV regularisers (and the photometric L1) are differentiated inside
+    dnr_raster_bwd.  The same step with the losses' own backward kernels writing gradient images (fuse_loss_backward =
+    False) and with host-resident float maps (the generic torch path of get_loss_dict) must give the same loss and the
+    same parameter gradients."""
+    from dn_splatter_b200.losses import DepthLossType
+
+    params, cam = scene_and_camera(1200, 144, 112, view=2)
+    H, W = 112, 144
+    g = torch.Generator().manual_seed(11)
+    depth = 2 + 6 * torch.rand(H, W, 1, generator=g)
+    depth[torch.rand(H, W, 1, generator=g) < 0.1] = 0.0
+    raw = {"image": (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8), "mono_depth": depth,
+           "normal": (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8)}
+    kw = dict(use_depth_loss=True, depth_lambda=0.2, depth_loss_type=DepthLossType(depth_type), ssim_lambda=ssim_lambda)
+    runs = {}
+    for name, fuse, dev in (("fused", True, "cuda"), ("images", False, "cuda"), ("host", True, "cpu")):
+        m = _model(params, fuse_loss_backward=fuse, **kw)
+        batch = {k: v.to(dev) for k, v in raw.items()}
+        out = m.get_outputs(_camera(cam))
+        ld = m.get_loss_dict(out, batch)
+        (ld["main_loss"] + ld["scale_reg"]).backward()
+        runs[name] = (float(ld["main_loss"]), {k: m.gauss_params[k].grad.clone() for k in
+                                                ("means", "quats", "scales", "opacities", "features_dc", "features_rest")},
+                      m.xys_flat.absgrad.clone())
+        if name == "fused":  # nothing was left undelivered, and the deferred specs were consumed by the raster backward
+            assert "deferred" not in m.raster_out.info
+    for other in ("images", "host"):
+        assert abs(runs["fused"][0] - runs[other][0]) <= 2e-6 * max(1.0, abs(runs[other][0])), other
+        for k, want in runs[other][1].items():
+            rel = float((runs["fused"][1][k] - want).norm() / (want.norm() + 1e-30))
+            assert rel < 2e-4, (other, k, rel)
+        ab = runs[other][2]
+        assert float((runs["fused"][2] - ab).abs().max()) <= 2e-4 * float(ab.abs().max() + 1e-30)

@@ -150,7 +150,7 @@ def test_precise_hit_lists_render_bit_identical_images(case):
     a single bit of any output, and the kept list must be an order-preserving sub-list of gsplat's."""
     params, cam = scene_and_camera(**case)
     _, full = cuda_outputs(params, cam, exact_lists=True)
-    _, cut = cuda_outputs(params, cam)
+    _, cut = cuda_outputs(params, cam, list_shift=0)
     for name in ("rgb", "depth", "normal", "alpha", "surface_normal"):
         assert torch.equal(getattr(full, name), getattr(cut, name)), f"{name} differs between exact and precise-hit lists"
     assert torch.equal(full.tiles_per_gauss, cut.tiles_per_gauss)  # API output stays gsplat's bbox count
@@ -160,6 +160,87 @@ def test_precise_hit_lists_render_bit_identical_images(case):
     for t in range(len(fo) - 1):
         it = iter(ff[fo[t]:fo[t + 1]])
         assert all(g in it for g in cf[co[t]:co[t + 1]]), f"tile {t}: kept list is not a sub-sequence"
+
+
+@needs_cuda
+@pytest.mark.parametrize("case", CASES + [dict(n=20000, width=320, height=240, view=2)])
+def test_supertile_lists_and_kernel_variants_render_bit_identical_images(case):
+    """Lists kept per 32/64/128-pixel supertile (each 16x16 tile filters its supertile's list inside the raster kernels)
+    and the scalar-arithmetic variant must not change a single bit of any output; the backward must agree with the
+    per-tile-list backward up to the order of its float atomics, for every reduction / arithmetic variant."""
+    params, cam = scene_and_camera(**case)
+    _, full = cuda_outputs(params, cam, exact_lists=True)
+    pr, ref = cuda_outputs(params, cam, requires_grad=True, list_shift=0)
+    _loss(ref.rgb, ref.depth, ref.normal, ref.alpha).backward()
+    seen = []
+    for shift, variant in ((1, 0), (2, 0), (3, 0), (2, 1), (2, 2), (2, 3), (0, 2)):
+        stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+        p, out = cuda_outputs(params, cam, requires_grad=True, list_shift=shift, variant=variant, stats=stats)
+        for name in ("rgb", "depth", "normal", "alpha", "surface_normal"):
+            assert torch.equal(getattr(full, name), getattr(out, name)), f"{name}: list_shift={shift} variant={variant}"
+        assert out.info["list_tile"] == 16 << shift
+        _loss(out.rgb, out.depth, out.normal, out.alpha).backward()
+        for k in p:
+            rel = float((p[k].grad - pr[k].grad).norm() / (pr[k].grad.norm() + 1e-30))
+            assert rel < 1e-4, (k, rel, shift, variant)
+        ab = ref.means2d.absgrad
+        assert float((out.means2d.absgrad - ab).abs().max()) <= 1e-4 * float(ab.abs().max() + 1e-30)
+        walked_f, kept_f, walked_b, kept_b = stats.tolist()
+        assert 0 < kept_f <= walked_f and 0 < kept_b <= walked_b and kept_b <= kept_f
+        seen.append((shift, out.info["n_isects"]))
+    by_shift = dict(seen)
+    assert by_shift[3] <= by_shift[2] <= by_shift[1] <= ref.info["n_isects"]  # coarser lists hold fewer pairs
+
+
+@needs_cuda
+@pytest.mark.parametrize("case", CASES[:2])
+def test_touched_only_project_bwd_matches_dense(case):
+    """project_bwd over the Gaussians flagged by raster_bwd (default) == the dense kernel."""
+    params, cam = scene_and_camera(**case)
+    pa, a = cuda_outputs(params, cam, requires_grad=True, touched_bwd=False)
+    pb, b = cuda_outputs(params, cam, requires_grad=True, touched_bwd=True)
+    _loss(a.rgb, a.depth, a.normal, a.alpha).backward()
+    _loss(b.rgb, b.depth, b.normal, b.alpha).backward()
+    for k in pa:
+        rel = float((pa[k].grad - pb[k].grad).norm() / (pa[k].grad.norm() + 1e-30))
+        assert rel < 1e-4, (k, rel)
+    for attr in ("grad", "absgrad"):
+        x, y = getattr(a.means2d, attr), getattr(b.means2d, attr)
+        assert float((x - y).abs().max()) <= 1e-4 * float(x.abs().max() + 1e-30)
+
+
+@needs_cuda
+def test_capacity_overflow_is_loud_and_recoverable():
+    """sync-free sizing: a view that needs more slots than 1.15 x the largest count seen so far must never hand out
+    gradients — its backward raises DnrCapacityError, the capacity grows, and the repeated view is exact."""
+    import dn_splatter_b200.rasterize as R
+
+    small, cam = scene_and_camera(4000, 208, 160, view=1, scale_mult=0.3)
+    big, _ = scene_and_camera(4000, 208, 160, view=1, scale_mult=3.0)
+    for _ in range(3):  # two seeding views (synchronous), then sync-free
+        cuda_outputs(small, cam, sync_free=True)
+    _, ref = cuda_outputs(big, cam)
+    p, out = cuda_outputs(big, cam, requires_grad=True, sync_free=True)
+    assert int(out.info["n_isects_dev"]) > out.info["n_isects"], "the test scene must overflow the seeded capacity"
+    with pytest.raises(R.DnrCapacityError):
+        _loss(out.rgb, out.depth, out.normal, out.alpha).backward()
+    assert all(v.grad is None for v in p.values())
+    p, out = cuda_outputs(big, cam, requires_grad=True, sync_free=True)  # capacity was raised: exact now
+    for name in ("rgb", "depth", "normal", "alpha"):
+        assert torch.equal(getattr(out, name), getattr(ref, name))
+    _loss(out.rgb, out.depth, out.normal, out.alpha).backward()
+    # a truncated no-grad render is reported by the next call instead
+    R._CAPACITY.clear()
+    for _ in range(3):
+        cuda_outputs(small, cam, sync_free=True)
+    with torch.no_grad():
+        cuda_outputs(big, cam, sync_free=True)
+        torch.cuda.synchronize()
+        with pytest.raises(R.DnrCapacityError):
+            cuda_outputs(big, cam, sync_free=True)
+        _, again = cuda_outputs(big, cam, sync_free=True)
+    assert torch.equal(again.rgb, ref.rgb)
+    R._CAPACITY.clear()
 
 
 @needs_cuda

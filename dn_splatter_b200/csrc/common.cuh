@@ -143,7 +143,16 @@ template <bool PK> __device__ __forceinline__ V2<PK> dnr_power2x2(float a, float
   return fma2(v2<PK>(dx), t1, mul2(dy, t2));
 }
 
-// Can the splat (record head q0 = {x, y, a', b'}, q1 = {c', opac, nthr, -}) reach alpha >= 1/255 at any pixel centre of
+// Does tile (tx, ty) belong to the splat's gsplat tile box (dnr_tile_box of its 3-sigma radius, same float operations)?
+// gsplat composites a splat only in the tiles of that box — also where a pixel just outside it would still pass the
+// alpha test — so a 16x16 tile that walks a coarser supertile list has to apply the box itself to stay bit-identical.
+__device__ __forceinline__ bool dnr_in_tile_box(const float4& q0, const float4& q1, int tx, int ty) {
+  const float r = q1.w * (1.0f / DNR_TILE), tcx = q0.x * (1.0f / DNR_TILE), tcy = q0.y * (1.0f / DNR_TILE);
+  const float fx = (float)tx, fy = (float)ty;
+  return fx >= floorf(tcx - r) && fx < ceilf(tcx + r) && fy >= floorf(tcy - r) && fy < ceilf(tcy + r);
+}
+
+// Can the splat (record head q0 = {x, y, a', b'}, q1 = {c', opac, nthr, radius}) reach alpha >= 1/255 at any pixel centre of
 // the rectangle [cx0, cx1] x [cy0, cy1]?  The log2-domain exponent p(dx,dy) = a' dx^2 + b' dx dy + c' dy^2 is concave
 // with its maximum 0 at the centre, so its maximum over the rectangle is 0 when the centre lies inside and otherwise
 // sits on one of the four edges, where it is a 1-D parabola.  Conservative: slack on the threshold, and anything

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const DnrArgs a) {
   // pre-test "power < nthr => alpha < 1/255" (the exact alpha test still decides; 1e-3 slack keeps it conservative)
   const float nthr = -log2f(255.0f * op) - 1e-3f;
   rec[0] = make_float4(g.mx, g.my, (-0.5f * DNR_LOG2E) * conA, (-DNR_LOG2E) * conB);
-  rec[1] = make_float4((-0.5f * DNR_LOG2E) * conC, op, nthr, 0.f);
+  rec[1] = make_float4((-0.5f * DNR_LOG2E) * conC, op, nthr, (float)g.radius);  // radius: the raster kernels' tile-box test
   rec[2] = make_float4(col[0], col[1], col[2], g.mc[2]);
   if (NORMALS) rec[3] = make_float4(nc[0], nc[1], nc[2], 0.f);
 }

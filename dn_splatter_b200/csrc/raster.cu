@@ -59,8 +59,10 @@ __device__ __forceinline__ void issue_chunk(const float* __restrict__ records, c
 // Tile filter over a landed chunk: survivors' chunk slots, in list order, into sidx[0..total).  Called by all NT
 // threads; contains two __syncthreads().
 template <int REC, int NT>
-__device__ __forceinline__ int filter_chunk(const float* stage_smem, int n_c, float cx0, float cx1, float cy0, float cy1,
-                                            unsigned char* sidx, int* scnt, int tid) {
+__device__ __forceinline__ int filter_chunk(const float* stage_smem, int n_c, int tile_x, int tile_y, unsigned char* sidx,
+                                            int* scnt, int tid) {
+  const float cx0 = (float)(tile_x * DNR_TILE) + 0.5f, cy0 = (float)(tile_y * DNR_TILE) + 0.5f;
+  const float cx1 = cx0 + (float)(DNR_TILE - 1), cy1 = cy0 + (float)(DNR_TILE - 1);
   constexpr int PER = CH / NT;  // entries per thread
   constexpr int NW = NT / 32;
   const int lane = tid & 31, warp = tid >> 5;
@@ -71,7 +73,10 @@ __device__ __forceinline__ int filter_chunk(const float* stage_smem, int n_c, fl
     // warp w tests entries [w*32*PER, (w+1)*32*PER), 32 at a time: ascending slot order within and across warps
     const int t = (warp * PER + k) * 32 + lane;
     bool hit = false;
-    if (t < n_c) hit = dnr_tile_hit(r4[t * (REC / 4) + 0], r4[t * (REC / 4) + 1], cx0, cx1, cy0, cy1);
+    if (t < n_c) {
+      const float4 q0 = r4[t * (REC / 4) + 0], q1 = r4[t * (REC / 4) + 1];
+      hit = dnr_in_tile_box(q0, q1, tile_x, tile_y) && dnr_tile_hit(q0, q1, cx0, cx1, cy0, cy1);
+    }
     m[k] = __ballot_sync(0xffffffffu, hit);
   }
   if (lane == 0) {
@@ -118,7 +123,6 @@ __global__ void __launch_bounds__(FWD_THREADS) raster_fwd_kernel(const DnrArgs a
   const bool in0 = (i0 < a.height) && (j < a.width), in1 = (i1 < a.height) && (j < a.width);
   const float px = (float)j + 0.5f;
   const V2<PK> npy = v2<PK>(-((float)i0 + 0.5f), -((float)i1 + 0.5f));
-  const float cx0 = (float)(blockIdx.x * DNR_TILE) + 0.5f, cy0 = (float)(blockIdx.y * DNR_TILE) + 0.5f;
   const int start = a.tile_offsets[stile], end = a.tile_offsets[stile + 1];
   const int n = end - start;
   const int nchunks = (n + CH - 1) / CH;
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(FWD_THREADS) raster_fwd_kernel(const DnrArgs a
     mbar_wait(&bars[stage], (uint32_t)((c >> 1) & 1));
     consumed = c + 1;
     const int n_c = min(CH, n - c * CH);
-    const int total = filter_chunk<REC, FWD_THREADS>(recs[stage], n_c, cx0, cx0 + 15.0f, cy0, cy0 + 15.0f, sidx, scnt, tid);
+    const int total = filter_chunk<REC, FWD_THREADS>(recs[stage], n_c, blockIdx.x, blockIdx.y, sidx, scnt, tid);
     walked += n_c; kept += total;
     const float4* r4 = reinterpret_cast<const float4*>(recs[stage]);
     const int base = start + c * CH;
@@ -361,9 +365,15 @@ __device__ __forceinline__ float transpose_reduce16(const float (&v)[16], float*
   // the rows of the upper half-warp sit 16 floats further: at step r the two half-warps read rows r and 16 + r whose
   // bank offsets differ by 16, so the 32 lanes hit 32 distinct banks, and every offset below is an immediate
   const float* col = scr + (lane & 15) + (lane >> 4) * (16 * RED_STRIDE + 16);
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four chains: the adds do not wait on each other's latency
 #pragma unroll
-  for (int r = 0; r < 16; ++r) s += col[r * RED_STRIDE];
+  for (int r = 0; r < 16; r += 4) {
+    s0 += col[r * RED_STRIDE];
+    s1 += col[(r + 1) * RED_STRIDE];
+    s2 += col[(r + 2) * RED_STRIDE];
+    s3 += col[(r + 3) * RED_STRIDE];
+  }
+  const float s = (s0 + s1) + (s2 + s3);
   return s + __shfl_xor_sync(0xffffffffu, s, 16);
 }
 
@@ -385,7 +395,6 @@ __global__ void __launch_bounds__(BWD_THREADS) raster_bwd_kernel(const DnrArgs a
   const int shift = a.list_shift;
   const int stile = (blockIdx.y >> shift) * stiles_x + (blockIdx.x >> shift);
   const int start = a.tile_offsets[stile], end = a.tile_offsets[stile + 1];
-  const float cx0 = (float)(blockIdx.x * DNR_TILE) + 0.5f, cy0 = (float)(blockIdx.y * DNR_TILE) + 0.5f;
 
   // ---- per-pixel state and the gradient of the glue (P1/P3 backward) ----
   // warp -> 16 wide x 8 tall strip; lane -> column lane & 15, rows (lane >> 4) + {0, 2, 4, 6}: pixel pairs A = rows
@@ -492,7 +501,7 @@ __global__ void __launch_bounds__(BWD_THREADS) raster_bwd_kernel(const DnrArgs a
       issue_chunk<REC, BWD_THREADS>(a.records, a.flatten_ids, chi - CH - 1, -1, min(CH, chi - CH - start), recs[stage ^ 1],
                                     ids_s[stage ^ 1], &bars[stage ^ 1], tid);
     mbar_wait(&bars[stage], (uint32_t)((c >> 1) & 1));
-    const int total = filter_chunk<REC, BWD_THREADS>(recs[stage], n_c, cx0, cx0 + 15.0f, cy0, cy0 + 15.0f, sidx, scnt, tid);
+    const int total = filter_chunk<REC, BWD_THREADS>(recs[stage], n_c, blockIdx.x, blockIdx.y, sidx, scnt, tid);
     walked += n_c; kept += total;
     const float4* r4 = reinterpret_cast<const float4*>(recs[stage]);
     for (int s = 0; s < total; ++s) {

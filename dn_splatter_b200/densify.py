@@ -67,6 +67,16 @@ class DensifyState:
         all_reduce_densification_stats(self.xys_grad_norm, self.vis_counts, self.max_2Dsize, group)
         self.vis_counts -= float(dist.get_world_size(group) - 1)
 
+    def all_reduce_before_refinement(self, step: int, warmup_length: int, group=None) -> bool:
+        """What a multi-rank training loop calls at a refine_every boundary, right before refinement_after: reduces ONLY
+        when that call will consume and reset the statistics (step > warmup_length).  During warm-up refinement_after
+        returns without resetting; an in-place reduction there would be reduced again at the next boundary and the early
+        steps would end up weighted by world_size^k."""
+        if step <= warmup_length:
+            return False
+        self.all_reduce_(group)
+        return True
+
     @torch.no_grad()
     def after_train(self, absgrad: Tensor, radii: Tensor, last_size) -> None:
         """absgrad [N,2] (means2d.absgrad of the view just trained), radii [N] int32, last_size (H, W).  Mask-free

@@ -28,13 +28,12 @@ METHODS: Dict[str, Dict] = {
         "model": lambda: DNSplatterModelConfig(regularization_strategy="dn-splatter"),
     },
     "ags-mesh": {
-        "description": "AGS-Mesh: adaptive Gaussian splatting and meshing",
+        "description": "AGS-Mesh variant of Splatfacto model. Incorporates depth and normal filtering strategy.",
         "model": lambda: DNSplatterModelConfig(regularization_strategy="ags-mesh"),
     },
     "dn-splatter-big": {  # dn_config.py:137-198 (:150-153): lower cull threshold, no culling after stop_split_at
         "description": "DN-Splatter Big variant",
-        "model": lambda: DNSplatterModelConfig(regularization_strategy="dn-splatter", cull_alpha_thresh=0.005,
-                                               continue_cull_post_densification=False),
+        "model": lambda: DNSplatterModelConfig(cull_alpha_thresh=0.005, continue_cull_post_densification=False),
     },
 }
 TRAINER_DEFAULTS = dict(steps_per_eval_image=500, steps_per_eval_batch=500, steps_per_save=1000000,
@@ -42,9 +41,61 @@ TRAINER_DEFAULTS = dict(steps_per_eval_image=500, steps_per_eval_batch=500, step
                         gradient_accumulation_steps={"camera_opt": 100, "color": 10, "shs": 10})
 
 
-def method_specifications():
-    """nerfstudio MethodSpecification objects (only when nerfstudio is installed)."""
-    from nerfstudio.plugins.types import MethodSpecification  # noqa: F401  (raises ImportError otherwise)
+def method_specifications(datamanager_config=None):
+    """The three nerfstudio MethodSpecification objects of the reference's dn_config.py (`dn_splatter`, `ags_mesh`,
+    `dn_splatter_big`; entry points of its pyproject.toml:27-42), with THIS package's pipeline and model configs.
 
-    raise NotImplementedError("nerfstudio is not part of this image; wire METHODS into TrainerConfig where it exists "
-                              "(INTEGRATION.md shows the three-line registration)")
+    Needs nerfstudio (absent from this image: ImportError).  `datamanager_config`: the datamanager config every method
+    uses; default = the reference's own data stack when it is installed next to nerfstudio
+    (DNSplatterManagerConfig(dataparser=NormalNerfstudioConfig(load_3D_points=True)), dn_config.py:24-27) — data parsing is
+    outside this package's scope (SURVEY §2 out-of-scope rows).  Register in the host package's pyproject.toml:
+
+        [project.entry-points.'nerfstudio.method_configs']
+        dn-splatter = 'dn_splatter_b200.dn_config:dn_splatter'
+    """
+    from nerfstudio.configs.base_config import ViewerConfig
+    from nerfstudio.engine.optimizers import AdamOptimizerConfig
+    from nerfstudio.engine.schedulers import ExponentialDecaySchedulerConfig
+    from nerfstudio.engine.trainer import TrainerConfig
+    from nerfstudio.plugins.types import MethodSpecification
+
+    from .dn_pipeline import DNSplatterPipelineConfig
+
+    def datamanager():
+        if datamanager_config is not None:
+            import copy
+
+            return copy.deepcopy(datamanager_config)
+        from dn_splatter.data.normal_nerfstudio import NormalNerfstudioConfig  # the reference's data stack
+        from dn_splatter.dn_datamanager import DNSplatterManagerConfig
+
+        return DNSplatterManagerConfig(dataparser=NormalNerfstudioConfig(load_3D_points=True))
+
+    def optimizers():
+        out = {}
+        for name, g in optimizer_groups().items():
+            sched = (ExponentialDecaySchedulerConfig(lr_final=g["lr_final"], max_steps=g["max_steps"])
+                     if g["lr_final"] is not None else None)
+            out[name] = {"optimizer": AdamOptimizerConfig(lr=g["lr"], eps=g["eps"]), "scheduler": sched}
+        return out
+
+    specs = {}
+    for name, m in METHODS.items():
+        trainer_kw = dict(TRAINER_DEFAULTS)
+        if name == "dn-splatter-big":  # the reference's big variant sets no gradient accumulation (dn_config.py:137-146)
+            trainer_kw.pop("gradient_accumulation_steps")
+        specs[name] = MethodSpecification(
+            config=TrainerConfig(method_name=name, pipeline=DNSplatterPipelineConfig(datamanager=datamanager(), model=m["model"]()),
+                                 optimizers=optimizers(), viewer=ViewerConfig(num_rays_per_chunk=1 << 15), vis="viewer",
+                                 **trainer_kw),
+            description=m["description"])
+    return specs
+
+
+def __getattr__(name):
+    """`dn_splatter`, `ags_mesh`, `dn_splatter_big`: module attributes for nerfstudio's entry points, built lazily so that
+    importing this module never requires nerfstudio."""
+    key = {"dn_splatter": "dn-splatter", "ags_mesh": "ags-mesh", "dn_splatter_big": "dn-splatter-big"}.get(name)
+    if key is None:
+        raise AttributeError(name)
+    return method_specifications()[key]

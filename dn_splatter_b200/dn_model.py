@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from torch import Tensor
 
 from .cameras import Cameras, is_camera
-from .losses import DepthLoss, DepthLossType, TVLoss
+from .losses import DepthLoss, DepthLossType, TVLoss, ssim  # noqa: F401  (ssim re-exported)
 from .rasterize import dn_rasterize, get_viewmat, raster_holder, to_device_async
 from .regularization_strategy import AGSMeshRegularization, DNRegularization, FusedL1, FusedSSIM, u8_to_float
 from .utils.normal_utils import normal_from_depth_image
@@ -91,8 +91,27 @@ def matrix_to_quaternion(M: Tensor) -> Tensor:
     return q / (2.0 * torch.sqrt(d))[:, None]
 
 
+try:  # nerfstudio is optional: with it the config / model classes below extend Splatfacto's, as the reference's do
+    from nerfstudio.cameras.camera_optimizers import CameraOptimizerConfig  # type: ignore
+    from nerfstudio.models.splatfacto import SplatfactoModel as _ModelBase  # type: ignore
+    from nerfstudio.models.splatfacto import SplatfactoModelConfig as _ConfigBase  # type: ignore
+
+    HAVE_NERFSTUDIO = True
+except Exception:  # noqa: BLE001
+    HAVE_NERFSTUDIO = False
+    _ModelBase = torch.nn.Module
+
+    @dataclass
+    class CameraOptimizerConfig:  # stand-in with the one field the hot path reads (nerfstudio CameraOptimizerConfig.mode)
+        mode: Literal["off", "SO3xR3", "SE3"] = "off"
+
+    @dataclass
+    class _ConfigBase:  # no inherited fields: they are spelled out below with nerfstudio 1.1.3's defaults
+        pass
+
+
 @dataclass
-class DNSplatterModelConfig:
+class DNSplatterModelConfig(_ConfigBase):
     """Field names and defaults of the reference's DNSplatterModelConfig (dn_model.py:55-123) plus the
     inherited SplatfactoModelConfig fields [EXT] that the hot path reads.  Dead fields are kept for API
     compatibility and do nothing, exactly as in the reference."""
@@ -123,7 +142,8 @@ class DNSplatterModelConfig:
     use_scale_regularization: bool = False
     max_gauss_ratio: float = 5.0
     stop_split_at: int = 15000
-    camera_optimizer_mode: str = "off"
+    camera_optimizer: CameraOptimizerConfig = field(default_factory=lambda: CameraOptimizerConfig(mode="off"))
+    """Config of the camera optimizer to use (reference dn_model.py:113-116); only mode == "off" is accelerated."""
     output_depth_during_training: bool = True
     pearson_lambda: float = 0
     # ---- inherited splatfacto fields [EXT nerfstudio 1.1.3 defaults] ----
@@ -162,49 +182,34 @@ class DNSplatterModelConfig:
     list_shift: int = 2
     """Intersection lists per (16 << list_shift)-pixel supertile (see csrc/binning.cu); ignored with exact_isect_lists."""
 
+    @property
+    def camera_optimizer_mode(self) -> str:  # round-1 name of the field
+        return getattr(self.camera_optimizer, "mode", "off")
+
     def setup(self, **kwargs):
         return self._target(self, **kwargs)
 
 
-def _gaussian_window(size: int, sigma: float, device, dtype) -> Tensor:
-    x = torch.arange(size, device=device, dtype=dtype) - (size - 1) / 2
-    g = torch.exp(-(x * x) / (2 * sigma * sigma))
-    return g / g.sum()
-
-
-def ssim(img1: Tensor, img2: Tensor, kernel_size: int = 11, sigma: float = 1.5, data_range: float = 1.0) -> Tensor:
-    """Mean SSIM of [1,C,H,W] images, Gaussian 11x11 window, reflect padding then crop — what
-    torchmetrics.StructuralSimilarityIndexMeasure(data_range=1.0, kernel_size=11) computes [EXT]
-    (reference dn_model.py:180).  Plain torch: the photometric loss is SURVEY §8f-3 'next', not the hot path."""
-    C = img1.shape[1]
-    pad = (kernel_size - 1) // 2
-    g = _gaussian_window(kernel_size, sigma, img1.device, img1.dtype)
-    win = (g[:, None] * g[None, :]).expand(C, 1, kernel_size, kernel_size).contiguous()
-    a, b = F.pad(img1, (pad,) * 4, mode="reflect"), F.pad(img2, (pad,) * 4, mode="reflect")
-    stack = torch.cat([a, b, a * a, b * b, a * b], dim=0)
-    mu = F.conv2d(stack, win, groups=C)
-    mu1, mu2, s11, s22, s12 = mu.chunk(5, dim=0)
-    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
-    v1, v2, v12 = s11 - mu1 * mu1, s22 - mu2 * mu2, s12 - mu1 * mu2
-    m = ((2 * mu1 * mu2 + c1) * (2 * v12 + c2)) / ((mu1 * mu1 + mu2 * mu2 + c1) * (v1 + v2 + c2))
-    return m[..., pad:-pad, pad:-pad].mean()
-
-
-class DNSplatterModel(torch.nn.Module):
+class DNSplatterModel(_ModelBase):
     """Depth + Normal splatter on the B200 rasterizer."""
 
     config: DNSplatterModelConfig
 
     def __init__(self, config: DNSplatterModelConfig, seed_points: Optional[Tuple[Tensor, ...]] = None,
                  num_train_data: int = 1, device: Union[str, torch.device] = "cuda", **kwargs):
-        super().__init__()
-        self.config = config
-        self.seed_points = seed_points
-        self.num_train_data = num_train_data
-        self.kwargs = kwargs
         self._init_device = torch.device(device)
         self._bucket = None
-        self.populate_modules()
+        if HAVE_NERFSTUDIO:
+            # SplatfactoModel.__init__ stores seed_points, Model.__init__ stores config / scene_box / num_train_data and
+            # calls populate_modules() (ours); callbacks, param groups, metrics and the viewer hooks come from the base
+            super().__init__(config, kwargs.pop("scene_box", None), num_train_data, seed_points=seed_points, **kwargs)
+        else:
+            super().__init__()
+            self.config = config
+            self.seed_points = seed_points
+            self.num_train_data = num_train_data
+            self.kwargs = kwargs
+            self.populate_modules()
         self.to(self._init_device)
 
     def load_gaussians(self, params: Dict[str, Tensor]) -> None:

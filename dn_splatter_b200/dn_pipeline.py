@@ -15,9 +15,22 @@ import torch.distributed as dist
 from .dn_model import DNSplatterModel, DNSplatterModelConfig
 from .parallel import FlatGradBucket
 
+try:  # with nerfstudio the classes extend VanillaPipeline(Config), exactly as the reference's do (dn_pipeline.py:36-66)
+    from nerfstudio.pipelines.base_pipeline import VanillaPipeline as _PipelineBase  # type: ignore
+    from nerfstudio.pipelines.base_pipeline import VanillaPipelineConfig as _PipelineConfigBase  # type: ignore
+
+    HAVE_NERFSTUDIO = True
+except Exception:  # noqa: BLE001
+    HAVE_NERFSTUDIO = False
+    _PipelineBase = torch.nn.Module
+
+    @dataclass
+    class _PipelineConfigBase:
+        pass
+
 
 @dataclass
-class DNSplatterPipelineConfig:
+class DNSplatterPipelineConfig(_PipelineConfigBase):
     _target: Type = field(default_factory=lambda: DNSplatterPipeline)
     datamanager: Any = None  # object with .setup(device=, test_mode=, world_size=, local_rank=) or a ready datamanager
     model: DNSplatterModelConfig = field(default_factory=DNSplatterModelConfig)
@@ -30,7 +43,7 @@ class DNSplatterPipelineConfig:
         return self._target(self, **kwargs)
 
 
-class DNSplatterPipeline(torch.nn.Module):
+class DNSplatterPipeline(_PipelineBase):
     """Datamanager contract: `next_train(step) -> (camera, batch)` with the batch keys of the reference's
     DNSplatterDataManager (image, mask, sensor_depth, mono_depth, normal, confidence; dn_datamanager.py:90-150),
     optional `train_dataparser_outputs.metadata`, `train_dataset` (len + optional scene_box/metadata)."""
@@ -38,7 +51,8 @@ class DNSplatterPipeline(torch.nn.Module):
     def __init__(self, config: DNSplatterPipelineConfig, device: str,
                  test_mode: Literal["test", "val", "inference"] = "val", world_size: int = 1, local_rank: int = 0,
                  grad_scaler=None):
-        super().__init__()
+        # like the reference (dn_pipeline.py:76): skip VanillaPipeline.__init__, which would build its own datamanager / DDP
+        (super(_PipelineBase, self) if HAVE_NERFSTUDIO else super()).__init__()
         self.config, self.test_mode = config, test_mode
         dm = config.datamanager
         if hasattr(dm, "setup"):

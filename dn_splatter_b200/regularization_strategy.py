@@ -332,8 +332,12 @@ class DNRegularization(RegularizationStrategy):
             gt_img = kwargs.get("gt_img") if self.depth_loss_type == DepthLossType.EdgeAwareLogL1 else None
             return _FusedDNLoss.apply(pred_depth, None, gt_depth, None, gt_img, _FUSED_DEPTH[self.depth_loss_type],
                                       self.depth_lambda, self.depth_tolerance, False)
-        if self.depth_loss_type == DepthLossType.PearsonDepth:
-            raise NotImplementedError("PearsonDepth pairs with LocalPearsonDepthLoss, which is out of scope")
+        if self.depth_loss_type == DepthLossType.PearsonDepth:  # reference :167-176 (global + lambda * local Pearson)
+            n_valid = valid.sum()
+            glob = (self.depth_loss(pred_depth, gt_depth.float()) * n_valid) / n_valid
+            local = (DepthLoss(DepthLossType.LocalPearsonDepthLoss)(pred_depth, gt_depth.float()) * n_valid) / n_valid
+            d = glob + self.depth_lambda * local
+            return d + self.depth_lambda * d  # quirk B6
         d = self.depth_loss(pred_depth[valid], gt_depth[valid].float())
         return d + self.depth_lambda * d  # quirk B6
 

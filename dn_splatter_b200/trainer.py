@@ -60,8 +60,9 @@ class Trainer:
             st = m.__dict__.get("_densify_state")
             # Reduce ONLY when refinement_after will consume (and reset) the statistics: during warm-up it returns without
             # resetting them, and an in-place all-reduce there would be summed again at the next boundary (weight W^k).
-            if self.world_size > 1 and st is not None and step > m.config.warmup_length:
-                st.all_reduce_()  # identical statistics -> identical decisions (and identical split samples: same seed)
+            if self.world_size > 1 and st is not None:
+                # identical statistics -> identical decisions (and identical split samples: same seed)
+                st.all_reduce_before_refinement(step, m.config.warmup_length)
             info = m.refinement_after(self.optimizers, step, generator=self.generator)
         self.step += 1
         return {"loss": loss.detach(), "refine": info}

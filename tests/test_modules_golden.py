@@ -32,8 +32,6 @@ def test_loss_modules_match_reference(z):
     assert isinstance(NormalLoss(NormalLossType.Smooth).loss, TVLoss) and isinstance(NormalLoss(NormalLossType.L1).loss, L1)
     with pytest.raises(ValueError):
         DepthLoss("nope")
-    with pytest.raises(NotImplementedError):
-        DepthLoss(DepthLossType.LocalPearsonDepthLoss)
 
 
 def test_find_edges_and_angular_error_match_reference(z):

@@ -114,3 +114,53 @@ def test_two_rank_densification_statistics_equal_single_rank():
     torch.testing.assert_close(got[0], st.xys_grad_norm, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(got[1], st.vis_counts)
     torch.testing.assert_close(got[2], st.max_2Dsize)
+
+
+def _warmup_worker(rank, world, port, ret):
+    """The Trainer's schedule around the warm-up boundary: after_train every step, a refine boundary every 2 steps,
+    warm-up of 5 steps; refinement_after is modelled by what it does to the statistics (reset once step > warm-up)."""
+    from dn_splatter_b200.densify import DensifyState
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    st, warmup, consumed = DensifyState(), 5, []
+    for step in range(9):
+        absgrad, radii = _fake_view_stats(step * world + rank)
+        st.after_train(absgrad, radii, (48, 64))
+        if step > 0 and step % 2 == 0:
+            if st.all_reduce_before_refinement(step, warmup):
+                consumed.append((step, st.xys_grad_norm.clone(), st.vis_counts.clone(), st.max_2Dsize.clone()))
+                st.reset()
+    if rank == 0:
+        ret.put(consumed)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_statistics_are_not_re_reduced_during_warmup():
+    """reducing in place at every boundary of the warm-up (where nothing resets the statistics) weighted the
+    first steps by world_size^k.  The statistics the first real refinement consumes must equal the single-process ones."""
+    from dn_splatter_b200.densify import DensifyState
+
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_warmup_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert [g[0] for g in got] == [6, 8]  # boundaries 2 and 4 lie inside the warm-up: no reduction there
+    st = DensifyState()
+    for step in range(7):  # steps 0..6 on both ranks feed the first refinement
+        for r in range(world):
+            st.after_train(*_fake_view_stats(step * world + r), (48, 64))
+    torch.testing.assert_close(got[0][1], st.xys_grad_norm, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(got[0][2], st.vis_counts)
+    torch.testing.assert_close(got[0][3], st.max_2Dsize)

@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--list-shift", type=int, default=2, help="intersection lists per (16 << s)-pixel supertile")
     ap.add_argument("--variant", type=int, default=0, help="raster kernel tuning knob (A/B timing)")
     ap.add_argument("--no-fused-loss-bwd", action="store_true", help="loss gradients as images from separate kernels (A/B)")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="multi-rank: dense NCCL all-reduce of the bucket + Adam instead "
+                                                                  "of the peer-memory reduction fused into the Adam pass")
     ap.add_argument("--epochs", type=int, default=5, help="extra, untimed-by-contract measurement: median ms/view over this "
                                                           "many passes over ALL views (0 = skip)")
     return ap.parse_args()
@@ -148,7 +150,13 @@ def build_workload(args, device, normals: bool):
     model.background_color = torch.tensor([0.1490, 0.1647, 0.2157])
     model.step = 30000  # full SH degree (sh_degree_interval schedule done)
     model.train()
-    bucket = model.enable_flat_grads()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    peer = world > 1 and not args.nccl_allreduce and not args.no_optimizer
+    try:
+        bucket = model.enable_flat_grads(peer=peer)
+    except Exception as exc:  # noqa: BLE001 — no symmetric memory on this box: keep the NCCL path and say so
+        print(f"[bench] peer-memory bucket unavailable ({type(exc).__name__}: {exc}); using NCCL all-reduce", file=sys.stderr)
+        bucket = model.enable_flat_grads(peer=False)
     model.__dict__["_raster_variant"] = args.variant
     cams = [Cameras(c["c2w"][None], c["fx"], c["fy"], c["cx"], c["cy"], c["width"], c["height"],
                     metadata={"cam_idx": i}) for i, c in enumerate(ring_cameras(args.views, args.width, args.height))]
@@ -188,6 +196,9 @@ def run_step(model, bucket, cam, batch, reduce=True, optimizer=None):
     loss_dict = model.get_loss_dict(outputs, dict(batch))
     loss = loss_dict["main_loss"] + loss_dict["scale_reg"]
     loss.backward()
+    if reduce and optimizer is not None and hasattr(bucket, "peer_flat"):
+        optimizer.step_reduce(bucket)
+        return loss
     if reduce:
         bucket.all_reduce()
     if optimizer is not None:
@@ -282,7 +293,9 @@ def workload_config(args, normals, world, sample=None):
         "losses": ("0.8 L1 + 0.2 (1-SSIM) rgb (the reference's default ssim_lambda)" if ssim else "L1 rgb")
                   + " + DNRegularization(EdgeAwareLogL1 depth (1+0.2), L1+TV normal, min-scale)",
         "optimizer": "Adam over the six parameter groups with the reference's learning rates, inside the step" if opt else "not in the step",
-        "parallelism": f"per-camera sharding x{world}, one flat all-reduce/step" if world > 1 else "single GPU",
+        "parallelism": (f"per-camera sharding x{world}, " + ("dense NCCL all-reduce of the gradient bucket, then Adam"
+                        if (args.nccl_allreduce or args.no_optimizer) else "gradient rows gathered over NVLink peer memory inside the Adam pass"))
+                       if world > 1 else "single GPU",
         "l2_policy": "inputs larger than L2 (236 MB parameters + 236 MB gradients + 472 MB Adam moments per step; a different "
                      "view and supervision set every step)",
         "gt_sets": args.gt_sets, "view_order": "step s renders view (37 s) mod views of the rank's shard (the ring is sampled evenly)",
@@ -351,8 +364,14 @@ def main():
 
     graphed = None
 
+    peer_reduce = hasattr(bucket, "peer_flat")
+
     def finish_step():
-        """What follows the (captured) forward + backward: gradient all-reduce, then the Adam step."""
+        """What follows the (captured) forward + backward: gradient reduction and the Adam step — one fused pass over
+        NVLink peer memory (dnr_adam_step_reduce), or NCCL all-reduce then Adam."""
+        if peer_reduce:
+            optimizer.step_reduce(bucket)
+            return
         bucket.all_reduce()
         if optimizer is not None:
             optimizer.step()

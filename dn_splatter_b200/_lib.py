@@ -54,6 +54,16 @@ class DnrAdamSeg(C.Structure):
                 ("bc1", C.c_double), ("bc2_sqrt", C.c_double)]
 
 
+PEER_MAX = 8
+
+
+class DnrPeerReduce(C.Structure):
+    """Mirror of struct DnrPeerReduce (include/dnr.h)."""
+
+    _fields_ = [("world", _i), ("rank", _i), ("n_gauss", _i), ("reserved", _i), ("peer_flat", _p * PEER_MAX),
+                ("peer_touched", _p * PEER_MAX), ("mask", _p)]
+
+
 class DnrKnnGrid(C.Structure):
     """Mirror of struct DnrKnnGrid (include/dnr.h)."""
 
@@ -70,7 +80,7 @@ KERNELS_PER_CALL = {
     "dnr_finalize_fwd": (1, 0), "dnr_normal_from_depth": (1, 0), "dnr_raster_bwd": (1, 0), "dnr_project_bwd": (1, 0),
     "dnr_loss_fwd": (2, 0), "dnr_loss_bwd": (1, 0), "dnr_scale_loss_fwd": (1, 0), "dnr_scale_loss_bwd": (1, 0),
     "dnr_l1_fwd": (1, 0), "dnr_l1_bwd": (1, 0), "dnr_u8_to_f32": (1, 0),
-    "dnr_ssim_fwd": (1, 0), "dnr_ssim_bwd": (1, 0), "dnr_adam_step": (1, 0),
+    "dnr_ssim_fwd": (1, 0), "dnr_ssim_bwd": (1, 0), "dnr_ssim_fwd_ex": (1, 0), "dnr_ssim_bwd_ex": (1, 0), "dnr_photometric_fwd": (2, 0), "dnr_photometric_bwd": (1, 0), "dnr_adam_step": (1, 0), "dnr_adam_step_reduce": (2, 0),
     "dnr_knn_build": (2, 1), "dnr_knn_query": (1, 0), "dnr_density": (1, 0), "dnr_ray_densities": (1, 0),
 }
 LAUNCHES = {"handwritten": 0, "cub": 0}
@@ -137,8 +147,22 @@ def load():
     lib.dnr_u8_to_f32.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     lib.dnr_ssim_fwd.restype = C.c_int
     lib.dnr_ssim_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dnr_ssim_fwd_ex.restype = C.c_int
+    lib.dnr_ssim_fwd_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]
+    lib.dnr_ssim_bwd_ex.restype = C.c_int
+    lib.dnr_ssim_bwd_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
+    lib.dnr_photometric_fwd.restype = C.c_int
+    lib.dnr_photometric_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
+    lib.dnr_photometric_bwd.restype = C.c_int
+    lib.dnr_photometric_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dnr_adam_step.restype = C.c_int
     lib.dnr_adam_step.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p]
+    lib.dnr_adam_step_reduce.restype = C.c_int
+    lib.dnr_adam_step_reduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
     lib.dnr_knn_workspace_bytes.restype = C.c_int64
     lib.dnr_knn_workspace_bytes.argtypes = [C.c_int32, C.c_void_p]
     lib.dnr_knn_build.restype = C.c_int
@@ -169,7 +193,7 @@ EXPORTS = (
     "dnr_version", "dnr_error_string", "dnr_project_fwd", "dnr_bin_scan_workspace_bytes", "dnr_bin_scan",
     "dnr_bin_sort_workspace_bytes", "dnr_bin_sort", "dnr_depth_order_ptr", "dnr_raster_fwd", "dnr_finalize_fwd", "dnr_normal_from_depth",
     "dnr_raster_bwd", "dnr_project_bwd", "dnr_loss_fwd", "dnr_loss_bwd", "dnr_scale_loss_fwd", "dnr_scale_loss_bwd",
-    "dnr_l1_fwd", "dnr_l1_bwd", "dnr_u8_to_f32", "dnr_ssim_fwd", "dnr_ssim_bwd", "dnr_adam_step", "dnr_knn_workspace_bytes", "dnr_knn_build", "dnr_knn_query",
+    "dnr_l1_fwd", "dnr_l1_bwd", "dnr_u8_to_f32", "dnr_ssim_fwd", "dnr_ssim_bwd", "dnr_ssim_fwd_ex", "dnr_ssim_bwd_ex", "dnr_photometric_fwd", "dnr_photometric_bwd", "dnr_adam_step", "dnr_adam_step_reduce", "dnr_knn_workspace_bytes", "dnr_knn_build", "dnr_knn_query",
     "dnr_density", "dnr_ray_densities",
 )
 

@@ -47,15 +47,14 @@ def _stale(target: str, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = nvcc_path()
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "dnr.h"), os.path.abspath(__file__)]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "loss_common.cuh"), os.path.join(HERE, "..", "include", "dnr.h"), os.path.abspath(__file__)]
     objs = []
     for src, extra in SOURCES.items():
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            defs = [f"-D{k}={os.environ[k]}" for k in ("DNR_BWD_PPT", "DNR_EMIT_ROWWISE") if k in os.environ]  # tuning knobs
-            cmd = [nvcc, *ARCH, *COMMON, *extra, *defs, "-c", s, "-o", o]
+            cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)

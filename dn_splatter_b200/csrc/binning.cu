@@ -169,19 +169,6 @@ __device__ __forceinline__ HitGauss load_hit_gauss(const DnrArgs& a, const int32
   return h;
 }
 
-__device__ __forceinline__ HitGauss bcast_hit_gauss(const HitGauss& h, int src) {
-  HitGauss o;
-  o.g = __shfl_sync(0xffffffffu, h.g, src); o.radius = __shfl_sync(0xffffffffu, h.radius, src);
-  o.x0 = __shfl_sync(0xffffffffu, h.x0, src); o.y0 = __shfl_sync(0xffffffffu, h.y0, src);
-  o.nx = __shfl_sync(0xffffffffu, h.nx, src); o.ny = __shfl_sync(0xffffffffu, h.ny, src);
-  o.mx = __shfl_sync(0xffffffffu, h.mx, src); o.my = __shfl_sync(0xffffffffu, h.my, src);
-  o.A = __shfl_sync(0xffffffffu, h.A, src); o.B = __shfl_sync(0xffffffffu, h.B, src);
-  o.invA = __shfl_sync(0xffffffffu, h.invA, src); o.bac = __shfl_sync(0xffffffffu, h.bac, src);
-  o.twoAL = __shfl_sync(0xffffffffu, h.twoAL, src); o.ex_max = __shfl_sync(0xffffffffu, h.ex_max, src);
-  o.ey_max = __shfl_sync(0xffffffffu, h.ey_max, src); o.ey_star = __shfl_sync(0xffffffffu, h.ey_star, src);
-  return o;
-}
-
 // Tiles [lo, hi) of tile-row `ty` that the Gaussian can reach (empty when hi <= lo); `exact` keeps the whole box row.
 __device__ __forceinline__ void row_span(const HitGauss& h, int ty, bool exact, int ts, int& lo, int& hi) {
   lo = h.x0; hi = h.x0 + h.nx;
@@ -221,76 +208,34 @@ __global__ void __launch_bounds__(256) count_kernel(const DnrArgs a, const int32
   counts[i] = (i < a.n_gauss) ? cnt : 0;
 }
 
-// One warp per EMIT_GPW depth-sorted Gaussians (their parameters are loaded one per lane, in parallel); for each Gaussian
-// the lanes take its tile rows, compute the row spans, scan their lengths and write the spans (row-major, ascending x:
-// the order gsplat emits).  Few Gaussians per warp = more warps in flight: the kernel is latency-bound.  Entries past
-// the capacity are dropped (the caller sees n_isects_dev > capacity and retries).
-constexpr int EMIT_GPW = 8;
-#ifndef DNR_EMIT_ROWWISE
-#define DNR_EMIT_ROWWISE 0
-#endif
-
+// One lane per depth-sorted Gaussian (like count_kernel): it recomputes its row spans and writes its (list id, Gaussian
+// id) pairs at [isect_start[i], isect_start[i+1]) — row-major, ascending x: the order gsplat emits.  At supertile
+// granularity a Gaussian emits ~4-5 pairs, and neighbouring lanes (consecutive in depth order) own neighbouring output
+// ranges, so the small per-lane stores of a warp land in a few contiguous sectors.  (Round 1 walked 8 Gaussians per warp
+// with lanes over tile rows: 149 us at 1.8 M pairs, dominated by the per-Gaussian shuffle / ballot choreography.)
+// Entries past the capacity are dropped; n_isects_dev keeps the true count and the caller raises (DnrCapacityError).
 template <typename KeyT>
 __global__ void __launch_bounds__(256) emit_kernel(const DnrArgs a, const int32_t* __restrict__ order,
                                                   const int64_t* __restrict__ isect_start, KeyT* __restrict__ keys,
                                                   int32_t* __restrict__ gids, int tiles_x, int tiles_y) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int base = warp * EMIT_GPW;
-  if (base >= a.n_gauss) return;
-  const bool loader = lane < EMIT_GPW && base + lane < a.n_gauss;
-  const HitGauss mine = load_hit_gauss(a, order, loader ? base + lane : a.n_gauss, tiles_x, tiles_y);
-  const int64_t my_start = loader ? isect_start[base + lane] : 0;
-  const int64_t my_end = loader ? isect_start[base + lane + 1] : 0;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_gauss) return;
+  int64_t dst = isect_start[i];
+  const int64_t dst_end = isect_start[i + 1];
+  if (dst_end <= dst) return;
+  const HitGauss h = load_hit_gauss(a, order, i, tiles_x, tiles_y);
   const int64_t cap = a.n_isects;
   const bool exact = (a.flags & DNR_FLAG_EXACT_LISTS) != 0;
   const int ts = DNR_TILE << a.list_shift;
-  unsigned todo = __ballot_sync(0xffffffffu, my_end > my_start);
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const HitGauss h = bcast_hit_gauss(mine, src);
-    int64_t dst0 = __shfl_sync(0xffffffffu, my_start, src);
-    for (int r0 = 0; r0 < h.ny; r0 += 32) {
-      const int r = r0 + lane;
-      int lo = 0, hi = 0;
-      if (r < h.ny) row_span(h, h.y0 + r, exact, ts, lo, hi);
-      const int len = max(hi - lo, 0);
-      int incl = len;  // inclusive warp scan of the span lengths
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+  for (int r = 0; r < h.ny; ++r) {
+    int lo, hi;
+    row_span(h, h.y0 + r, exact, ts, lo, hi);
+    const int row_key = (h.y0 + r) * tiles_x;
+    for (int x = lo; x < hi; ++x, ++dst) {
+      if (dst < cap) {
+        keys[dst] = (KeyT)(row_key + x);
+        gids[dst] = h.g;
       }
-#if DNR_EMIT_ROWWISE
-      // round-2 candidate (not yet validated on a GPU, off by default): walk the rows uniformly and let the lanes write
-      // one row's span side by side -> contiguous 2 B / 4 B stores (1-2 sectors per row instead of one per lane).
-      // profiles/launches_r1d_step.txt: emit_kernel is 189 us for 69 MB, i.e. bound by partial-sector store transactions.
-      const int rows_here = min(32, h.ny - r0);
-      for (int rr = 0; rr < rows_here; ++rr) {
-        const int len_r = __shfl_sync(0xffffffffu, len, rr);
-        if (len_r == 0) continue;
-        const int lo_r = __shfl_sync(0xffffffffu, lo, rr);
-        const int64_t dst_r = dst0 + __shfl_sync(0xffffffffu, incl - len, rr);
-        const int key_r = (h.y0 + r0 + rr) * tiles_x + lo_r;
-        for (int k = lane; k < len_r; k += 32) {
-          if (dst_r + k < cap) {
-            keys[dst_r + k] = (KeyT)(key_r + k);
-            gids[dst_r + k] = h.g;
-          }
-        }
-      }
-#else
-      const int64_t dst = dst0 + (incl - len);
-      const int row_key = (h.y0 + r) * tiles_x;
-      for (int k = 0; k < len; ++k) {
-        if (dst + k < cap) {
-          keys[dst + k] = (KeyT)(row_key + lo + k);
-          gids[dst + k] = h.g;
-        }
-      }
-#endif
-      dst0 += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
 }
@@ -335,8 +280,7 @@ int bin_sort_impl(const DnrArgs* a, cudaStream_t s, int n_tiles, int tile_bits) 
   const int64_t cap = a->n_isects;
   SortWs<KeyT> w = carve_sort<KeyT>(a->ws_sort, cap, tile_bits);
   if (cap > 0) {
-    const int64_t threads = (((int64_t)a->n_gauss + EMIT_GPW - 1) / EMIT_GPW) * 32;  // one warp per EMIT_GPW Gaussians
-    emit_kernel<KeyT><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(*a, sw.order, sw.isect_start, w.keys_in, w.gids_in,
+    emit_kernel<KeyT><<<(unsigned)((a->n_gauss + 255) / 256), 256, 0, s>>>(*a, sw.order, sw.isect_start, w.keys_in, w.gids_in,
                                                                           tiles_x, tiles_y);
     DNR_CHECK_LAUNCH();
     pad_kernel<KeyT><<<148 * 2, 256, 0, s>>>(w.keys_in, w.gids_in, a->n_isects_dev, cap, (KeyT)n_tiles);

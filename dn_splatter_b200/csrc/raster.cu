@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(FWD_THREADS) raster_fwd_kernel(const DnrArgs a
     ed_for_max = fmaxf(ed_for_max, ed);
     if (NORMALS) {
       const float n0 = (p ? hi(N0) : lo(N0)) + Tp, n1 = (p ? hi(N1) : lo(N1)) + Tp, n2 = (p ? hi(N2) : lo(N2)) + Tp;  // white bg (B1)
-      const float nn = sqrtf(n0 * n0 + n1 * n1 + n2 * n2);
+      const float nn = sqrtf(__fmaf_rn(n2, n2, __fmaf_rn(n1, n1, __fmul_rn(n0, n0))));  // explicit: identical in every instantiation
       a.normal_norm[pix] = nn;
       a.out_normal[pix * 3 + 0] = (n0 / nn + 1.0f) * 0.5f;
       a.out_normal[pix * 3 + 1] = (n1 / nn + 1.0f) * 0.5f;
@@ -265,48 +265,69 @@ __global__ void __launch_bounds__(FWD_THREADS) raster_fwd_kernel(const DnrArgs a
 
 // ------------------------------------------------------------------------------------------------ loss gradients
 // d(loss)/d(rgb, depth, normal) at pixel (i, j) of the losses listed in include/dnr.h under DNR_LOSS_FUSED_BWD; the same
-// formulas as loss_bwd_kernel / l1_bwd_kernel (csrc/image_ops.cu), which remain the unfused path.
+// formulas as loss_bwd_kernel / l1_bwd_kernel (csrc/image_ops.cu), which remain the unfused path.  Written for memory-
+// level parallelism: a CTA has only 64 threads, so every load is unconditional (neighbour indices are clamped into the
+// image: a clamped neighbour is the pixel itself and contributes sgn(0) = 0 to the TV term; the edge weights carry an
+// explicit 0/1 factor) and only warp-uniform configuration tests remain as branches — the loads of a pixel issue back
+// to back instead of one round trip per `if`.
 __device__ __forceinline__ void fused_loss_grads(const DnrArgs& a, int i, int j, float v_rgb[3], float& v_depth, float v_n[3]) {
   const int W = a.width, H = a.height;
   const int p = i * W + j;
+  const int jr = min(j + 1, W - 1), jl = max(j - 1, 0), id = min(i + 1, H - 1), iu = max(i - 1, 0);
+  const int pr = i * W + jr, pl = i * W + jl, pd = id * W + j, pu = iu * W + j;
+  const float vl = a.v_loss ? __ldg(a.v_loss) : 1.0f;
   if (a.v_l1 != nullptr) {
     const float s = __ldg(a.v_l1) / (3.0f * (float)H * (float)W);
+    float gt[3], pred[3];
+    if (a.loss_flags & DNR_LOSS_IMG_U8) {
+      const uint8_t* im = (const uint8_t*)a.gt_image;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float gt = (a.loss_flags & DNR_LOSS_IMG_U8) ? __fmul_rn((float)((const uint8_t*)a.gt_image)[p * 3 + c], 1.0f / 255.0f)
-                                                       : ((const float*)a.gt_image)[p * 3 + c];
-      v_rgb[c] += sgnf(a.out_rgb[p * 3 + c] - gt) * s;
+      for (int c = 0; c < 3; ++c) gt[c] = __fmul_rn((float)__ldg(im + p * 3 + c), 1.0f / 255.0f);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gt[c] = __ldg((const float*)a.gt_image + p * 3 + c);
     }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pred[c] = __ldg(a.out_rgb + p * 3 + c);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v_rgb[c] += sgnf(pred[c] - gt[c]) * s;
   }
-  const float vl = a.v_loss ? __ldg(a.v_loss) : 1.0f;
-  if (a.depth_loss_type != 0 && a.gt_depth[p] > a.depth_tolerance) {
-    const float e = a.out_depth[p] - a.gt_depth[p];
+  if (a.depth_loss_type != 0) {
+    const float gd = __ldg(a.gt_depth + p), od = __ldg(a.out_depth + p);
+    float w = 1.0f / __ldg(a.loss_partials + 1);
+    if (a.depth_loss_type == 1) {
+      const float wx = edge_weight(a, p, pr), wy = edge_weight(a, p, pd);  // exp(0) = 1 at the clamped border: masked below
+      w = (j < W - 1 ? wx : 0.f) / __ldg(a.loss_partials + 1) + (i < H - 1 ? wy : 0.f) / __ldg(a.loss_partials + 3);
+    }
+    const float e = od - gd;
     float dval;
     if (a.depth_loss_type == 1 || a.depth_loss_type == 2) dval = sgnf(e) / (1.0f + fabsf(e));
     else if (a.depth_loss_type == 3) dval = sgnf(e);
     else dval = 2.0f * e;
     const float scale = vl * (1.0f + a.depth_lambda);  // quirk B6: depth_loss += lambda * depth_loss
-    if (a.depth_loss_type == 1) {
-      float w = 0.f;
-      if (j < W - 1) w += edge_weight(a, p, p + 1) / a.loss_partials[1];
-      if (i < H - 1) w += edge_weight(a, p, p + W) / a.loss_partials[3];
-      v_depth += scale * dval * w;
-    } else {
-      v_depth += scale * dval / a.loss_partials[1];
-    }
+    v_depth += (gd > a.depth_tolerance) ? scale * dval * w : 0.f;
   }
   if (a.use_normal_loss) {
     const float inv_l1 = vl / (3.0f * (float)H * (float)W);
     const float inv_tx = (W > 1) ? vl / (3.0f * (float)H * (float)(W - 1)) : 0.f;
     const float inv_ty = (H > 1) ? vl / (3.0f * (float)(H - 1) * (float)W) : 0.f;
+    float n[3], nr[3], nl[3], nd[3], nu[3], gn[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float n = a.out_normal[p * 3 + c];
-      float g = sgnf(n - gt_normal_at(a, p * 3 + c)) * inv_l1;
-      if (j < W - 1) g += sgnf(n - a.out_normal[(p + 1) * 3 + c]) * inv_tx;
-      if (j > 0) g -= sgnf(a.out_normal[(p - 1) * 3 + c] - n) * inv_tx;
-      if (i < H - 1) g += sgnf(n - a.out_normal[(p + W) * 3 + c]) * inv_ty;
-      if (i > 0) g -= sgnf(a.out_normal[(p - W) * 3 + c] - n) * inv_ty;
+      n[c] = __ldg(a.out_normal + p * 3 + c);
+      nr[c] = __ldg(a.out_normal + pr * 3 + c);
+      nl[c] = __ldg(a.out_normal + pl * 3 + c);
+      nd[c] = __ldg(a.out_normal + pd * 3 + c);
+      nu[c] = __ldg(a.out_normal + pu * 3 + c);
+      gn[c] = gt_normal_at(a, p * 3 + c);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float g = sgnf(n[c] - gn[c]) * inv_l1;
+      g += sgnf(n[c] - nr[c]) * inv_tx;   // clamped neighbour == the pixel itself -> sgn(0) = 0
+      g -= sgnf(nl[c] - n[c]) * inv_tx;
+      g += sgnf(n[c] - nd[c]) * inv_ty;
+      g -= sgnf(nu[c] - n[c]) * inv_ty;
       v_n[c] += g;
     }
   }
@@ -379,7 +400,7 @@ __device__ __forceinline__ float transpose_reduce16(const float (&v)[16], float*
 
 // VARIANT: 0 = shared-memory transpose reduction, 1 = shuffle butterfly
 template <bool NORMALS, bool PK, int VARIANT>
-__global__ void __launch_bounds__(BWD_THREADS) raster_bwd_kernel(const DnrArgs a, int stiles_x) {
+__global__ void __launch_bounds__(BWD_THREADS, 9) raster_bwd_kernel(const DnrArgs a, int stiles_x) {
   constexpr int REC = NORMALS ? DNR_REC_FLOATS_N : DNR_REC_FLOATS;
   constexpr int RQ = REC / 4;
   constexpr int NW = BWD_THREADS / 32;
@@ -408,45 +429,49 @@ __global__ void __launch_bounds__(BWD_THREADS) raster_bwd_kernel(const DnrArgs a
   int wl = -1;
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    const int i = blockIdx.y * DNR_TILE + ly + 2 * p;
-    const bool inside = (i < a.height) && (j < a.width);
-    const int pix = inside ? i * a.width + j : 0;
-    last_id[p] = inside ? a.last_ids[pix] : -1;
-    wl = max(wl, last_id[p]);
-    float T_final = 1.f;
-    vC0[p] = vC1[p] = vC2[p] = vD[p] = vN0[p] = vN1[p] = vN2[p] = 0.f;
-    float va_cd = 0.f, va_n = 0.f;
-    if (inside) {
-      const float alpha = a.out_alpha[pix];
-      T_final = 1.0f - alpha;
-      float g_rgb[3] = {0.f, 0.f, 0.f}, g_d = 0.f, g_n[3] = {0.f, 0.f, 0.f};
-      if (a.loss_flags & DNR_LOSS_FUSED_BWD) fused_loss_grads(a, i, j, g_rgb, g_d, g_n);
-      if (a.v_rgb) { g_rgb[0] += a.v_rgb[pix * 3 + 0]; g_rgb[1] += a.v_rgb[pix * 3 + 1]; g_rgb[2] += a.v_rgb[pix * 3 + 2]; }
-      if (a.v_depth) g_d += a.v_depth[pix];
-      {
-        const uint8_t m = a.clamp_mask[pix];
-        vC0[p] = (m & 1) ? g_rgb[0] : 0.f;
-        vC1[p] = (m & 2) ? g_rgb[1] : 0.f;
-        vC2[p] = (m & 4) ? g_rgb[2] : 0.f;
-        va_cd -= a.background[0] * vC0[p] + a.background[1] * vC1[p] + a.background[2] * vC2[p];
-      }
-      if (a.v_alpha) va_cd += a.v_alpha[pix];
-      if (alpha > 0.f) {
-        const float ac = fmaxf(alpha, 1e-10f);
-        vD[p] = g_d / ac;
-        if (alpha >= 1e-10f) va_cd -= g_d * a.out_depth[pix] / ac;
-      }
-      if (NORMALS) {
-        if (a.v_normal) { g_n[0] += a.v_normal[pix * 3 + 0]; g_n[1] += a.v_normal[pix * 3 + 1]; g_n[2] += a.v_normal[pix * 3 + 2]; }
-        const float nn = a.normal_norm[pix];
-        const float n0 = 2.0f * a.out_normal[pix * 3 + 0] - 1.0f, n1 = 2.0f * a.out_normal[pix * 3 + 1] - 1.0f,
-                    n2 = 2.0f * a.out_normal[pix * 3 + 2] - 1.0f;
-        const float g0 = 0.5f * g_n[0], g1 = 0.5f * g_n[1], g2 = 0.5f * g_n[2];
-        const float dp = n0 * g0 + n1 * g1 + n2 * g2;
-        vN0[p] = (g0 - n0 * dp) / nn; vN1[p] = (g1 - n1 * dp) / nn; vN2[p] = (g2 - n2 * dp) / nn;
-        va_n = -(vN0[p] + vN1[p] + vN2[p]);
-      }
+    const int i_raw = blockIdx.y * DNR_TILE + ly + 2 * p;
+    const bool inside = (i_raw < a.height) && (j < a.width);
+    // pixels past the image edge read a valid pixel (clamped) and are masked out at the end: no load hides behind a branch
+    const int i = min(i_raw, a.height - 1), jc = min(j, a.width - 1);
+    const int pix = i * a.width + jc;
+    const int li = __ldg(a.last_ids + pix);
+    const float alpha = __ldg(a.out_alpha + pix);
+    const float odepth = __ldg(a.out_depth + pix);
+    const uint8_t m = __ldg(a.clamp_mask + pix);
+    float nn = 1.f, on0 = 0.f, on1 = 0.f, on2 = 0.f;
+    if (NORMALS) {
+      nn = __ldg(a.normal_norm + pix);
+      on0 = __ldg(a.out_normal + pix * 3 + 0); on1 = __ldg(a.out_normal + pix * 3 + 1); on2 = __ldg(a.out_normal + pix * 3 + 2);
     }
+    float g_rgb[3] = {0.f, 0.f, 0.f}, g_d = 0.f, g_n[3] = {0.f, 0.f, 0.f};
+    if (a.v_rgb) { g_rgb[0] = __ldg(a.v_rgb + pix * 3 + 0); g_rgb[1] = __ldg(a.v_rgb + pix * 3 + 1); g_rgb[2] = __ldg(a.v_rgb + pix * 3 + 2); }
+    if (a.v_depth) g_d = __ldg(a.v_depth + pix);
+    if (NORMALS && a.v_normal) { g_n[0] = __ldg(a.v_normal + pix * 3 + 0); g_n[1] = __ldg(a.v_normal + pix * 3 + 1); g_n[2] = __ldg(a.v_normal + pix * 3 + 2); }
+    const float g_a = a.v_alpha ? __ldg(a.v_alpha + pix) : 0.f;
+    if (a.loss_flags & DNR_LOSS_FUSED_BWD) fused_loss_grads(a, i, jc, g_rgb, g_d, g_n);
+
+    last_id[p] = inside ? li : -1;
+    wl = max(wl, last_id[p]);
+    const float T_final = inside ? 1.0f - alpha : 1.0f;
+    vC0[p] = (inside && (m & 1)) ? g_rgb[0] : 0.f;
+    vC1[p] = (inside && (m & 2)) ? g_rgb[1] : 0.f;
+    vC2[p] = (inside && (m & 4)) ? g_rgb[2] : 0.f;
+    float va_cd = g_a - (a.background[0] * vC0[p] + a.background[1] * vC1[p] + a.background[2] * vC2[p]);
+    const float ac = fmaxf(alpha, 1e-10f);
+    vD[p] = (inside && alpha > 0.f) ? g_d / ac : 0.f;
+    if (alpha >= 1e-10f) va_cd -= g_d * odepth / ac;
+    float va_n = 0.f;
+    vN0[p] = vN1[p] = vN2[p] = 0.f;
+    if (NORMALS) {
+      const float n0 = 2.0f * on0 - 1.0f, n1 = 2.0f * on1 - 1.0f, n2 = 2.0f * on2 - 1.0f;
+      const float g0 = 0.5f * g_n[0], g1 = 0.5f * g_n[1], g2 = 0.5f * g_n[2];
+      const float dp = n0 * g0 + n1 * g1 + n2 * g2;
+      vN0[p] = inside ? (g0 - n0 * dp) / nn : 0.f;
+      vN1[p] = inside ? (g1 - n1 * dp) / nn : 0.f;
+      vN2[p] = inside ? (g2 - n2 * dp) / nn : 0.f;
+      va_n = -(vN0[p] + vN1[p] + vN2[p]);
+    }
+    if (!inside) va_cd = 0.f;
     // d(out)/d(alpha_i) = sum_k (c_k T - B_k ra) v_k + T_final ra v_a, B_k = sum_{j>i} c_jk fac_j.  Only the contraction
     // S = sum_k B_k v_k is needed, and it is carried as S' = S - T_final v_a: one running scalar per gradient route.
     Tp[p] = T_final;
@@ -504,10 +529,13 @@ __global__ void __launch_bounds__(BWD_THREADS) raster_bwd_kernel(const DnrArgs a
     const int total = filter_chunk<REC, BWD_THREADS>(recs[stage], n_c, blockIdx.x, blockIdx.y, sidx, scnt, tid);
     walked += n_c; kept += total;
     const float4* r4 = reinterpret_cast<const float4*>(recs[stage]);
+    int t_next = total > 0 ? (int)sidx[0] : 0;
     for (int s = 0; s < total; ++s) {
-      const int t = sidx[s];
+      const int t = t_next;
+      if (s + 1 < total) t_next = sidx[s + 1];  // next survivor's slot: off the critical path of the next iteration
       const int pos = chi - 1 - t;
       if (pos > wl) continue;  // deeper than anything this warp composited (warp-uniform)
+      const int gid = ids_s[stage][t];  // for the RED at the end: loaded now, needed ~300 instructions later
       const float4 q0 = r4[t * RQ + 0];
       const float4 q1 = r4[t * RQ + 1];
       const float dx = q0.x - px;
@@ -595,14 +623,14 @@ __global__ void __launch_bounds__(BWD_THREADS) raster_bwd_kernel(const DnrArgs a
       for (int k = 0; k < 16; ++k) v[k] = lo(acc[k]) + hi(acc[k]);
       if (VARIANT == 0) {
         const float tot = transpose_reduce16(v, scr, lane) * post;
-        if (lane < 16 && tot != 0.f) atomicAdd(a.grad_records + (size_t)ids_s[stage][t] * DNR_GRAD_FLOATS + lane, tot);
+        if (lane < 16 && tot != 0.f) atomicAdd(a.grad_records + (size_t)gid * DNR_GRAD_FLOATS + lane, tot);
       } else {
         const float tot = butterfly16(v, lane);
         const int k = (lane >> 1) & 15;
         const float ps = (k == 0 || k == 1) ? -DNR_LN2 : ((k == 2 || k == 3) ? DNR_LN2 : ((k == 4 || k == 6) ? 0.5f : 1.0f));
-        if ((lane & 1) == 0 && tot != 0.f) atomicAdd(a.grad_records + (size_t)ids_s[stage][t] * DNR_GRAD_FLOATS + k, tot * ps);
+        if ((lane & 1) == 0 && tot != 0.f) atomicAdd(a.grad_records + (size_t)gid * DNR_GRAD_FLOATS + k, tot * ps);
       }
-      if (a.touched != nullptr && lane == 0) a.touched[ids_s[stage][t]] = 1;
+      if (a.touched != nullptr && lane == 0) a.touched[gid] = 1;
     }
     __syncthreads();  // stage, sidx and ids_s free for the chunk after next
   }

@@ -21,7 +21,8 @@ from torch import Tensor
 from .cameras import Cameras, is_camera
 from .losses import DepthLoss, DepthLossType, TVLoss, ssim  # noqa: F401  (ssim re-exported)
 from .rasterize import dn_rasterize, get_viewmat, raster_holder, to_device_async
-from .regularization_strategy import AGSMeshRegularization, DNRegularization, FusedL1, FusedSSIM, u8_to_float
+from .regularization_strategy import (AGSMeshRegularization, DNRegularization, FusedL1, FusedPhotometric, FusedSSIM,
+                                      u8_to_float)
 from .utils.normal_utils import normal_from_depth_image
 
 SH_C0 = 0.28209479177387814
@@ -222,13 +223,15 @@ class DNSplatterModel(_ModelBase):
         self.gauss_params = torch.nn.ParameterDict(new)
         self._bucket = None
 
-    def enable_flat_grads(self):
+    def enable_flat_grads(self, peer: bool = False, group=None):
         """Gradients of the six optimised parameter groups become views of ONE flat buffer that the
         rasterizer's backward accumulates into directly (no autograd copies) and that multi-GPU training
-        all-reduces with a single NCCL call (parallel.FlatGradBucket)."""
-        from .parallel import FlatGradBucket
+        all-reduces with a single NCCL call (parallel.FlatGradBucket) — or, with peer=True, that lives in NVLink-mapped
+        symmetric memory so that optim.FusedAdam.step_reduce can gather the gradient rows straight from the peers
+        (parallel.PeerGradBucket)."""
+        from .parallel import FlatGradBucket, PeerGradBucket
 
-        self._bucket = FlatGradBucket(dict(self.gauss_params))
+        self._bucket = PeerGradBucket(dict(self.gauss_params), group=group) if peer else FlatGradBucket(dict(self.gauss_params))
         return self._bucket
 
     # ------------------------------------------------------------------ init (reference :131-265)
@@ -348,19 +351,22 @@ class DNSplatterModel(_ModelBase):
         return self.background_color
 
     def _downscale_if_required(self, image: Tensor) -> Tensor:
+        """nerfstudio 1.1.3 splatfacto `resize_image` [EXT]: d x d box filter (conv2d with uniform weights, stride d)."""
         d = self._get_downscale_factor()
         if d > 1:
-            h, w = image.shape[0] // d, image.shape[1] // d
-            return F.interpolate(image.permute(2, 0, 1)[None].float(), size=(h, w), mode="bilinear", antialias=True)[0].permute(1, 2, 0)
+            image = image.to(torch.float32)
+            weight = (1.0 / (d * d)) * torch.ones((1, 1, d, d), dtype=torch.float32, device=image.device)
+            return F.conv2d(image.permute(2, 0, 1)[:, None, ...], weight, stride=d).squeeze(1).permute(1, 2, 0)
         return image
 
     def get_gt_img(self, image: Tensor, clamp_min: float = 0.0) -> Tensor:
+        """SplatfactoModel.get_gt_img [EXT]: uint8 -> float / 255, downscale, to the model's device; `clamp_min` is the
+        reference's `.clamp(min=10 / 255)` applied AFTER the resize (dn_model.py:633)."""
+        d = self._get_downscale_factor()
         if image.dtype == torch.uint8:
-            if image.device.type == "cuda":
-                image = u8_to_float(image, 255.0, clamp_min)  # one kernel instead of float() / 255 (/ clamp)
-                clamp_min = 0.0
-            else:
-                image = image.float() / 255.0
+            if image.device.type == "cuda" and d == 1:
+                return u8_to_float(image, 255.0, clamp_min).to(self.device)  # one kernel instead of float() / 255 / clamp
+            image = image.float() / 255.0
         image = self._downscale_if_required(image).to(self.device)
         return image.clamp(min=clamp_min) if clamp_min > 0.0 else image
 
@@ -475,6 +481,10 @@ class DNSplatterModel(_ModelBase):
         img = batch["image"]
         fused = ("mask" not in batch and img.shape[-1] == 3 and img.device == pred_img.device and pred_img.is_cuda
                  and self._get_downscale_factor() == 1)
+        if fused and cfg.ssim_lambda > 0 and cfg.fused_ssim and pred_img.shape[0] > 10 and pred_img.shape[1] > 10:
+            # (1 - l) L1 + l (1 - SSIM) in one kernel each way: pred receives a single gradient image
+            main = FusedPhotometric.apply(pred_img, img, cfg.ssim_lambda)
+            return {"main_loss": main, "scale_reg": self._scale_reg()}
         if fused:  # photometric L1 straight from the (uint8) image: one kernel forward, backward inside dnr_raster_bwd
             l1 = FusedL1.apply(pred_img, img, raster_holder(pred_img) if cfg.fuse_loss_backward else None)
             gt_img = None
@@ -487,20 +497,26 @@ class DNSplatterModel(_ModelBase):
             l1 = torch.abs(gt_img - pred_img).mean()
         main = (1 - cfg.ssim_lambda) * l1
         if cfg.ssim_lambda > 0:
-            if gt_img is None:
-                gt_img = self.get_gt_img(img)
             if cfg.fused_ssim and pred_img.is_cuda:
-                sim = FusedSSIM.apply(pred_img, gt_img)
+                # fused path: the uint8 image is read as stored (value / 255 inside the kernel)
+                sim = FusedSSIM.apply(pred_img, img if gt_img is None else gt_img)
             else:
+                if gt_img is None:
+                    gt_img = self.get_gt_img(img)
                 sim = ssim(gt_img.permute(2, 0, 1)[None], pred_img.permute(2, 0, 1)[None])
             main = main + cfg.ssim_lambda * (1 - sim)
+        return {"main_loss": main, "scale_reg": self._scale_reg()}
+
+    def _scale_reg(self) -> Tensor:
+        cfg = self.config
         if cfg.use_scale_regularization and self.step % 10 == 0:
             se = torch.exp(self.scales)
             reg = torch.clamp(se.amax(dim=-1) / se.amin(dim=-1), min=cfg.max_gauss_ratio) - cfg.max_gauss_ratio
-            scale_reg = 0.1 * reg.mean()
-        else:
-            scale_reg = torch.zeros((), device=self.device)
-        return {"main_loss": main, "scale_reg": scale_reg}
+            return 0.1 * reg.mean()
+        z = self.__dict__.get("_zero_scalar")
+        if z is None or z.device != self.device:
+            z = self.__dict__["_zero_scalar"] = torch.zeros((), device=self.device)
+        return z
 
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
         cfg = self.config

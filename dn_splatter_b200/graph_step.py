@@ -22,7 +22,7 @@ from typing import Dict, List, Optional
 import torch
 from torch import Tensor
 
-from .rasterize import DnrCapacityError, get_viewmat, suggested_capacity
+from .rasterize import DnrCapacityError, get_viewmat, round_capacity, suggested_capacity
 
 
 class GraphedTrainStep:
@@ -167,7 +167,7 @@ class GraphedTrainStep:
 
     def recapture(self, capacity: Optional[int] = None) -> None:
         """Re-captures the step with room for the largest count seen so far (x 1.15) or the given capacity."""
-        need = int(capacity) if capacity else ((int(self.max_count * 1.15) + 4096 + (1 << 19) - 1) >> 19) << 19
+        need = int(capacity) if capacity else round_capacity(int(self.max_count * 1.15) + 4096)
         self.capacity = max(self.capacity, need)
         self._count_pending = []
         torch.cuda.synchronize(self.device)

@@ -90,6 +90,35 @@ class FusedAdam(torch.optim.Optimizer):
         return loss
 
     @torch.no_grad()
+    def step_reduce(self, bucket):
+        """Multi-GPU step: gradient reduction over NVLink peer memory fused into the Adam pass (dnr_adam_step_reduce).
+        `bucket`: parallel.PeerGradBucket holding this model's gradients.  Equivalent to `bucket.all_reduce(); self.step()`
+        up to the order of the floating-point sum over ranks (here: rank order, identical on every replica)."""
+        segs = self._segments()
+        if not segs:
+            return
+        b1, b2 = segs[0][8], segs[0][9]
+        arr = (L.DnrAdamSeg * len(segs))()
+        widths = (ctypes.c_int32 * len(segs))()
+        lo, hi = bucket.flat.data_ptr(), bucket.flat.data_ptr() + bucket.flat.numel() * 4
+        for i, (p, g, m, v, lr, eps, bc1, bc2s, _, _) in enumerate(segs):
+            assert lo <= g.data_ptr() < hi, "parameter gradients must be views of the peer bucket"
+            assert p.is_contiguous() and m.is_contiguous() and v.is_contiguous() and p.shape[0] == bucket.n_gauss
+            arr[i].p, arr[i].g, arr[i].m, arr[i].v = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
+            arr[i].n, arr[i].lr, arr[i].eps, arr[i].bc1, arr[i].bc2_sqrt = p.numel(), lr, eps, bc1, bc2s
+            widths[i] = p.numel() // bucket.n_gauss
+        pr = L.DnrPeerReduce()
+        pr.world, pr.rank, pr.n_gauss = bucket.world, bucket.rank, bucket.n_gauss
+        for k in range(bucket.world):
+            pr.peer_flat[k], pr.peer_touched[k] = bucket.peer_flat[k], bucket.peer_touched[k]
+        pr.mask = bucket.mask.data_ptr()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        bucket.barrier()  # every rank's backward has finished writing its bucket and flags
+        L.check(L.load().dnr_adam_step_reduce(ctypes.cast(arr, ctypes.c_void_p), ctypes.cast(widths, ctypes.c_void_p), len(segs),
+                                              b1, b2, ctypes.byref(pr), stream), "dnr_adam_step_reduce")
+        bucket.barrier()  # nobody zeroes its bucket while a peer still reads it
+
+    @torch.no_grad()
     def reference_step(self):
         """The kernel's arithmetic restated in torch, operation for operation (csrc/adam.cu: adam_one) — used ONLY by the
         CPU test that pins the update rule against torch.optim.Adam; never called by the product path."""

@@ -56,6 +56,64 @@ class FlatGradBucket:
         return None
 
 
+class PeerGradBucket(FlatGradBucket):
+    """FlatGradBucket whose buffer — together with the per-Gaussian `touched` flags dnr_raster_bwd writes — lives in
+    NVLink-mapped symmetric memory (torch.distributed._symmetric_memory), so that every rank's kernels can read every
+    other rank's gradient rows directly.  `optim.FusedAdam.step_reduce(bucket)` then replaces the
+    `bucket.all_reduce(); optimizer.step()` pair with ONE pass that gathers, for each element, the rows of the ranks whose
+    view touched the Gaussian (sum in rank order: bit-identical on all replicas) and applies the Adam update — the
+    collective is fused into the consumer over peer memory instead of moving the dense 236 MB bucket through NCCL.
+
+    One view per rank and step (the flags describe the last backward).  Needs one process per GPU on a single NVLink
+    domain and an initialised NCCL process group."""
+
+    def __init__(self, params: Dict[str, torch.nn.Parameter], names: Iterable[str] = GRAD_PARAMS, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerGradBucket needs an initialised process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise RuntimeError("PeerGradBucket: at most 8 ranks (one NVLink domain)")
+        names = [n for n in names if n in params]
+        ps = {n: params[n] for n in names}
+        dev = next(iter(ps.values())).device
+        n_gauss = next(iter(ps.values())).shape[0]
+        total = sum(self._padded(p.numel()) for p in ps.values())
+        # one symmetric allocation: [flat gradients | touched flags (padded to 16 B)]
+        tbytes = (n_gauss + 15) // 16 * 16
+        raw = symm_mem.empty(total * 4 + tbytes, dtype=torch.uint8, device=dev)
+        self._handle = symm_mem.rendezvous(raw, self.group.group_name)
+        self._raw = raw
+        raw.zero_()
+        self.names, self.params = names, ps
+        self.flat = raw[: total * 4].view(torch.float32)
+        self.touched = raw[total * 4: total * 4 + n_gauss]
+        self.n_gauss, self._flat_bytes = n_gauss, total * 4
+        self.views: Dict[str, Tensor] = {}
+        off = 0
+        for n, p in ps.items():
+            v = self.flat[off:off + p.numel()].view_as(p)
+            p.grad = v
+            self.views[n] = v
+            off += self._padded(p.numel())
+        self.mask = torch.zeros(tbytes, dtype=torch.uint8, device=dev)
+        base = [int(x) for x in self._handle.buffer_ptrs]
+        self.peer_flat = base
+        self.peer_touched = [b + self._flat_bytes for b in base]
+        assert self.peer_flat[self.rank] == self.flat.data_ptr()
+
+    def sink(self) -> Dict[str, Tensor]:
+        out = dict(self.views)
+        out["touched"] = self.touched  # dn_rasterize writes the flags straight into the symmetric buffer
+        return out
+
+    def barrier(self) -> None:
+        """Cross-rank barrier on the current stream (device-side signal pads of the symmetric allocation)."""
+        self._handle.barrier(channel=0)
+
+
 def shard_views(n_views: int, rank: int, world_size: int) -> List[int]:
     """Round-robin view assignment: rank r renders {i : i mod world_size == r}."""
     return list(range(rank, n_views, world_size))

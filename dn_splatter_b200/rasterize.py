@@ -51,7 +51,7 @@ class _CapacityTracker:
         return self.seeds >= 2
 
     def capacity(self) -> int:
-        return ((int(self.max_seen * 1.15) + 4096 + (1 << 19) - 1) >> 19) << 19  # 512K-entry steps: allocator-friendly
+        return round_capacity(int(self.max_seen * 1.15) + 4096)
 
     def observe(self, n_isects_dev: Tensor, cap: int):
         """Queues the async read-back of this view's count; returns the ticket its backward checks."""
@@ -111,6 +111,14 @@ class _CapacityTracker:
 
 
 _CAPACITY: dict = {}
+
+
+def round_capacity(need: int) -> int:
+    """Rounds up keeping 4 significant bits (steps of 1/16 .. 1/8 of the value, at least 4096 entries): few distinct buffer
+    sizes for the caching allocator without over-allocating small scenes."""
+    need = max(int(need), 4096)
+    step = max(4096, 1 << max(need.bit_length() - 4, 0))
+    return (need + step - 1) // step * step
 
 
 def suggested_capacity(n_gauss: int, width: int, height: int, render_normals: bool = True, exact_lists: bool = False,
@@ -421,7 +429,10 @@ class _DnRasterize(torch.autograd.Function):
         keep = _apply_deferred_losses(a, ctx.holder.pop("deferred", None))
         touched = None
         if s.touched_bwd and not s.compact_bwd:
-            touched = torch.empty(n, dtype=torch.uint8, device=dev)
+            # the caller's buffer when it wants the flags (parallel.PeerGradBucket: peers read them over NVLink)
+            touched = ctx.grad_sink.get("touched") if ctx.grad_sink is not None else None
+            if touched is None:
+                touched = torch.empty(n, dtype=torch.uint8, device=dev)
             _set(a, touched=touched)
         L.check(_timed("raster_bwd", lib.dnr_raster_bwd, C.byref(a), st), "dnr_raster_bwd")
         del keep

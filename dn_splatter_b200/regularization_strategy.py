@@ -207,9 +207,10 @@ class FusedL1(torch.autograd.Function):
 
 
 class FusedSSIM(torch.autograd.Function):
-    """Mean SSIM of two [H,W,C] fp32 CUDA images (torchmetrics semantics, see dn_model.ssim) in one kernel each way;
-    differentiable w.r.t. `pred` only.  EXPERIMENTAL in round 1: enabled by DNSplatterModelConfig.fused_ssim; the torch
-    implementation dn_model.ssim() is its reference (tests/test_gpu_model.py::test_fused_ssim_matches_torch)."""
+    """Mean SSIM of two [H,W,C] CUDA images (torchmetrics semantics, see losses.ssim) in one kernel each way;
+    differentiable w.r.t. `pred` only.  `gt` is fp32 or uint8 (read as value / 255, as get_gt_img converts it).  Default
+    since round 2 (DNSplatterModelConfig.fused_ssim); losses.ssim() is its reference
+    (tests/test_gpu_model.py::test_fused_ssim_matches_torch)."""
 
     @staticmethod
     def forward(ctx, pred, gt):
@@ -217,13 +218,15 @@ class FusedSSIM(torch.autograd.Function):
         if pred.device.type != "cuda" or gt.device != pred.device:
             raise L.DnrError("FusedSSIM needs CUDA tensors on one device (no CPU path)")
         p = pred.detach().float().contiguous()
-        g = gt.detach().float().contiguous()
+        g = gt.detach().contiguous()
+        if g.dtype != torch.uint8:
+            g = g.float()
         assert p.dim() == 3 and p.shape == g.shape, "pred / gt must both be [H,W,C]"
         H, W, Cn = p.shape
         dmaps = torch.empty((3, H, W, Cn), dtype=torch.float32, device=p.device)
         out = torch.empty(1, dtype=torch.float32, device=p.device)
-        L.check(lib.dnr_ssim_fwd(p.data_ptr(), g.data_ptr(), H, W, Cn, dmaps.data_ptr(), out.data_ptr(), _stream()),
-                "dnr_ssim_fwd")
+        L.check(lib.dnr_ssim_fwd_ex(p.data_ptr(), g.data_ptr(), int(g.dtype == torch.uint8), H, W, Cn, dmaps.data_ptr(),
+                                    out.data_ptr(), _stream()), "dnr_ssim_fwd_ex")
         ctx.keep = (p, g, dmaps)
         ctx.fwd_stream = torch.cuda.current_stream()
         return out[0] / float((H - 10) * (W - 10) * Cn)
@@ -236,9 +239,48 @@ class FusedSSIM(torch.autograd.Function):
             v = v.detach().float().contiguous()
             vp = torch.empty_like(p)
             H, W, Cn = p.shape
-            L.check(lib.dnr_ssim_bwd(p.data_ptr(), g.data_ptr(), H, W, Cn, dmaps.data_ptr(), v.data_ptr(), vp.data_ptr(),
-                                     _stream()), "dnr_ssim_bwd")
+            L.check(lib.dnr_ssim_bwd_ex(p.data_ptr(), g.data_ptr(), int(g.dtype == torch.uint8), H, W, Cn, dmaps.data_ptr(),
+                                        v.data_ptr(), vp.data_ptr(), _stream()), "dnr_ssim_bwd_ex")
             return vp, None
+
+
+class FusedPhotometric(torch.autograd.Function):
+    """main = (1 - ssim_lambda) * mean|pred - gt| + ssim_lambda * (1 - mean SSIM(pred, gt)): the parent
+    SplatfactoModel's photometric loss (dn_model.py:624-628 -> [EXT]) in one kernel each way — the L1 sum rides on the
+    SSIM kernel's loads and its sign gradient is written by the SSIM backward, so `pred` receives ONE gradient image and
+    autograd has nothing to accumulate.  `gt`: [H,W,C] fp32 or uint8 (value / 255)."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, ssim_lambda: float):
+        lib = L.load()
+        if pred.device.type != "cuda" or gt.device != pred.device:
+            raise L.DnrError("FusedPhotometric needs CUDA tensors on one device (no CPU path)")
+        p = pred.detach().float().contiguous()
+        g = gt.detach().contiguous()
+        if g.dtype != torch.uint8:
+            g = g.float()
+        assert p.dim() == 3 and p.shape == g.shape, "pred / gt must both be [H,W,C]"
+        H, W, Cn = p.shape
+        dmaps = torch.empty((3, H, W, Cn), dtype=torch.float32, device=p.device)
+        out = torch.empty(3, dtype=torch.float32, device=p.device)
+        L.check(lib.dnr_photometric_fwd(p.data_ptr(), g.data_ptr(), int(g.dtype == torch.uint8), H, W, Cn, float(ssim_lambda),
+                                        dmaps.data_ptr(), out.data_ptr(), _stream()), "dnr_photometric_fwd")
+        ctx.keep = (p, g, dmaps)
+        ctx.lam = float(ssim_lambda)
+        ctx.fwd_stream = torch.cuda.current_stream()
+        return out[2].clone()
+
+    @staticmethod
+    def backward(ctx, v):
+        with torch.cuda.stream(ctx.fwd_stream):
+            lib = L.load()
+            p, g, dmaps = ctx.keep
+            v = v.detach().float().contiguous()
+            vp = torch.empty_like(p)
+            H, W, Cn = p.shape
+            L.check(lib.dnr_photometric_bwd(p.data_ptr(), g.data_ptr(), int(g.dtype == torch.uint8), H, W, Cn, ctx.lam,
+                                            dmaps.data_ptr(), v.data_ptr(), vp.data_ptr(), _stream()), "dnr_photometric_bwd")
+            return vp, None, None
 
 
 def u8_to_float(img: Tensor, divisor: float = 255.0, clamp_min: float = 0.0) -> Tensor:

@@ -230,11 +230,26 @@ int dnr_u8_to_f32(const uint8_t* src, int64_t n, float divisor, float clamp_min,
  * (H-10)x(W-10) interior.  pred / gt: [H,W,C] fp32.  fwd: *sum_out (zeroed by the call) = SUM of the SSIM map over
  * the interior and all channels (divide by (H-10)(W-10)C for the mean); dmaps [3,H,W,C] keeps the partial
  * derivatives for the backward.  bwd: v_pred[H,W,C] = (*v_mean or 1) * d(mean SSIM)/d(pred).
- * EXPERIMENTAL in round 1 (written after the GPU budget was spent; opt-in through fused_ssim). */
+ * Default since round 2 (DNSplatterModelConfig.fused_ssim). */
 int dnr_ssim_fwd(const float* pred, const float* gt, int32_t H, int32_t W, int32_t C, float* dmaps, float* sum_out,
                  void* stream);
 int dnr_ssim_bwd(const float* pred, const float* gt, int32_t H, int32_t W, int32_t C, const float* dmaps,
                  const float* v_mean, float* v_pred, void* stream);
+/* The same with the target read as stored: gt is uint8 (value / 255, as get_gt_img does) when gt_is_u8 != 0, else fp32. */
+int dnr_ssim_fwd_ex(const float* pred, const void* gt, int32_t gt_is_u8, int32_t H, int32_t W, int32_t C, float* dmaps,
+                    float* sum_out, void* stream);
+int dnr_ssim_bwd_ex(const float* pred, const void* gt, int32_t gt_is_u8, int32_t H, int32_t W, int32_t C, const float* dmaps,
+                    const float* v_mean, float* v_pred, void* stream);
+
+/* The whole photometric term of the parent SplatfactoModel.get_loss_dict [EXT] (dn_splatter/dn_model.py:624-628 calls it):
+ *   main = (1 - ssim_lambda) * mean|pred - gt| + ssim_lambda * (1 - mean SSIM)
+ * in one pass each way (the L1 sum shares the SSIM kernel's loads; its sign gradient is added by the SSIM backward).
+ * out (3 floats, zeroed by the call): [0] SSIM sum over the interior, [1] sum |pred - gt|, [2] main.
+ * bwd: v_pred[H,W,C] = (*v_main or 1) * d(main)/d(pred). */
+int dnr_photometric_fwd(const float* pred, const void* gt, int32_t gt_is_u8, int32_t H, int32_t W, int32_t C,
+                        float ssim_lambda, float* dmaps, float* out, void* stream);
+int dnr_photometric_bwd(const float* pred, const void* gt, int32_t gt_is_u8, int32_t H, int32_t W, int32_t C,
+                        float ssim_lambda, const float* dmaps, const float* v_main, float* v_pred, void* stream);
 
 /* One-launch Adam over all Gaussian parameter groups: replaces the per-group torch.optim.Adam instances of
  * dn_splatter/dn_config.py:29-68 (lr per group, eps 1e-15; betas (0.9, 0.999), no weight decay, no amsgrad).
@@ -250,6 +265,25 @@ typedef struct DnrAdamSeg {
   double lr, eps, bc1, bc2_sqrt; /* doubles: rounded to fp32 exactly where torch.optim.Adam rounds them */
 } DnrAdamSeg;
 int dnr_adam_step(const DnrAdamSeg* segs /* HOST array */, int32_t n_segs, double beta1, double beta2, void* stream);
+
+/* Multi-GPU: the gradient reduction fused into the Adam pass over NVLink peer memory (replaces the
+ * bucket.all_reduce() + optimizer.step() pair that stands in for the reference's DDP wrapper, dn_pipeline.py:123-128).
+ * Every rank keeps its flat gradient bucket and its `touched` flags (DnrArgs.touched, written by dnr_raster_bwd) in
+ * peer-mapped memory at the same offsets; rows of untouched Gaussians are exactly zero.  For each element the gradient
+ * is the sum, in rank order, of the rows of the ranks that touched the Gaussian (read straight from their memory), so
+ * all replicas apply bit-identical updates.  segs[i].g must point into THIS rank's bucket (peer_flat[rank]); widths[i] =
+ * floats per Gaussian of segment i.  The caller brackets the call with cross-rank barriers (all buckets final before,
+ * all reads done before anyone zeroes its bucket again). */
+#define DNR_PEER_MAX 8
+typedef struct DnrPeerReduce {
+  int32_t world, rank;
+  int32_t n_gauss, reserved;
+  const float* peer_flat[DNR_PEER_MAX];      /* device pointers valid on THIS device: rank k's flat bucket */
+  const uint8_t* peer_touched[DNR_PEER_MAX]; /* rank k's touched flags [n_gauss] */
+  uint8_t* mask;                             /* [n_gauss] local scratch (bit k: rank k touched the Gaussian) */
+} DnrPeerReduce;
+int dnr_adam_step_reduce(const DnrAdamSeg* segs /* HOST array */, const int32_t* widths /* HOST array */, int32_t n_segs,
+                         double beta1, double beta2, const DnrPeerReduce* peers /* HOST struct */, void* stream);
 
 /* ---- SuGaR-style queries (EXPERIMENTAL in round 1: opt-in through dn_splatter_b200.sugar) ----
  * Grid-hash k-NN: replaces sklearn behind dn_splatter/utils/knn.py:29-43 (knn_sk) and nerfstudio's k_nearest_sklearn

@@ -79,6 +79,7 @@ def project_gaussians(
     near_plane: float = 0.01,
     far_plane: float = 1e10,
     radius_clip: float = 0.0,
+    fov_size=None,
 ) -> Dict[str, Tensor]:
     """radii[N] i32, means2d[N,2], depths[N], conics[N,3], compensations[N].
     Culled Gaussians have radius 0 and zeroed float outputs (gsplat leaves them
@@ -111,8 +112,11 @@ def project_gaussians(
             Sc[j][i] = Sc[i][j]
 
     fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
-    tan_fovx = (0.5 * width) / fx
-    tan_fovy = (0.5 * height) / fy
+    # fov_size = (W, H) of the frame the 1.3 tan(fov) clamp refers to: set it to the FULL frame when rendering a crop window
+    # of a larger frame (tests/test_gpu_fullsize.py), so that the window's Gaussians see the full frame's Jacobian clamp
+    fw, fh = (width, height) if fov_size is None else fov_size
+    tan_fovx = (0.5 * fw) / fx
+    tan_fovy = (0.5 * fh) / fy
     lim_x = 1.3 * tan_fovx
     lim_y = 1.3 * tan_fovy
     zs = torch.where(in_depth, z, torch.ones_like(z))  # keep culled lanes finite
@@ -409,9 +413,10 @@ def rasterization(
     rasterize_mode: str = "classic",
     eps2d: float = 0.3,
     collect_absgrad: bool = False,
+    fov_size=None,
 ):
     """render[H,W,4] (rgb premultiplied, ED), alpha[H,W,1], info — dn_model.py:495-516."""
-    proj = project_gaussians(means, quats, scales, viewmat, K, width, height, eps2d, near_plane, far_plane)
+    proj = project_gaussians(means, quats, scales, viewmat, K, width, height, eps2d, near_plane, far_plane, fov_size=fov_size)
     radii = proj["radii"]
     opac = opacities
     if rasterize_mode == "antialiased":

@@ -97,3 +97,55 @@ def test_fullsize_backward_is_linear_and_bucket_matches_autograd(scene):
     for k, a in zip(names, g1):
         rel = float((leaf[k].grad - a).norm() / (a.norm() + 1e-30))
         assert rel < 1e-4, (k, rel)
+
+
+@needs_cuda
+def test_fullsize_window_matches_oracle(scene):
+    """at the full C2 size the CUDA path was only compared with itself.  Here a tile-aligned 256x192 window
+    around the principal point of the 1M-Gaussian 1080p frame is rendered by the CPU oracle (same camera, principal point
+    shifted into the window, the full frame's 1.3 tan(fov) clamp) and compared with the same window of the CUDA render:
+    images to the parity tolerances of tests/test_gpu_parity.py, and the gradient of a window-supported loss w.r.t. every
+    parameter of the Gaussians that reach the window."""
+    from dn_splatter_b200.synthetic import BACKGROUND
+    from oracle import dn_ref
+
+    torch.set_num_threads(min(8, torch.get_num_threads()))
+    params, vm, K, c2w, bg = scene
+    x0, y0, ww, wh = 832, 448, 256, 192  # multiples of 16: the window's tiles are the frame's tiles
+    g = torch.Generator().manual_seed(3)
+    wts = {k: torch.rand(wh, ww, c, generator=g) for k, c in (("rgb", 3), ("depth", 1), ("normal", 3), ("alpha", 1))}
+
+    p, out = _render(scene, requires_grad=True)
+    win = lambda t: t[y0:y0 + wh, x0:x0 + ww]  # noqa: E731
+    loss = sum((win(getattr(out, k)) * wts[k].cuda()).sum() for k in wts) * 1e-3
+    loss.backward()
+
+    pc = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in params.items()}
+    cam = dict(fx=float(K[0, 0]), fy=float(K[1, 1]), cx=float(K[0, 2]) - x0, cy=float(K[1, 2]) - y0)
+    ref = dn_ref.get_outputs(pc, c2w.cpu(), cam["fx"], cam["fy"], cam["cx"], cam["cy"], ww, wh, torch.tensor(BACKGROUND),
+                             fov_size=(W, H))
+    from tests.helpers import frac_close
+
+    for name, got, want in (("rgb", out.rgb, ref["rgb"]), ("normal", out.normal, ref["normal"]),
+                            ("alpha", out.alpha, ref["accumulation"])):
+        frac, mx = frac_close(win(got), want, atol=1e-4)
+        assert frac >= 0.999 and mx <= 2e-2, (name, frac, mx)
+    cov = ref["accumulation"] > 0  # the depth fill uses the frame-wide maximum: compare where something was composited
+    frac, mx = frac_close(win(out.depth)[cov], ref["depth"][cov], atol=1e-4, rtol=1e-5)
+    assert frac >= 0.999, ("depth", frac, mx)
+    # gradients of the window loss (the fill value is detached, uncovered pixels contribute no depth gradient)
+    lref = ((ref["rgb"] * wts["rgb"]).sum() + (torch.where(cov, ref["depth"], torch.zeros(())) * wts["depth"]).sum()
+            + (ref["normal"] * wts["normal"]).sum() + (ref["accumulation"] * wts["alpha"]).sum()) * 1e-3
+    # same masking on the CUDA side: recompute its loss with the uncovered depth pixels dropped
+    for v in p.values():
+        v.grad = None
+    p2, out2 = _render(scene, requires_grad=True)
+    covc = cov.cuda()
+    loss2 = ((win(out2.rgb) * wts["rgb"].cuda()).sum() + (torch.where(covc, win(out2.depth), torch.zeros((), device="cuda")) * wts["depth"].cuda()).sum()
+             + (win(out2.normal) * wts["normal"].cuda()).sum() + (win(out2.alpha) * wts["alpha"].cuda()).sum()) * 1e-3
+    loss2.backward()
+    lref.backward()
+    for k in ("means", "quats", "scales", "opacities", "features_dc", "features_rest"):
+        gc, gr = p2[k].grad.cpu(), pc[k].grad
+        rel = float((gc - gr).norm() / (gr.norm() + 1e-30))
+        assert rel < 5e-3, (k, rel)

@@ -243,6 +243,18 @@ def test_fused_ssim_matches_torch(hw):
     (gout,) = torch.autograd.grad(out, x)
     assert abs(float(out) - float(ref)) < 2e-5
     assert float((gout - gref).norm() / gref.norm()) < 1e-4
+    # uint8 target read as stored (value / 255), 1 and 4 channels (more than one channel group per CTA)
+    for C in (1, 3, 4):
+        xc = torch.rand(H, W, C, generator=g).cuda().requires_grad_(True)
+        y8 = (torch.rand(H, W, C, generator=g) * 255).to(torch.uint8).cuda()
+        yf = y8.float() / 255.0
+        ref = ssim(yf.permute(2, 0, 1)[None], xc.permute(2, 0, 1)[None])
+        (gref,) = torch.autograd.grad(ref, xc)
+        out = FusedSSIM.apply(xc, y8)
+        (gout,) = torch.autograd.grad(out, xc)
+        assert abs(float(out) - float(ref)) < 2e-5, C
+        # uncorrelated noise images are the worst case for the fp32 E[x^2] - mx^2 cancellation (in the torch reference too)
+        assert float((gout - gref).norm() / gref.norm()) < 1e-3, C
 
 
 @needs_cuda
@@ -308,3 +320,42 @@ def test_loss_gradients_fused_into_raster_bwd_match_the_gradient_image_path(dept
             assert rel < 2e-4, (other, k, rel)
         ab = runs[other][2]
         assert float((runs["fused"][2] - ab).abs().max()) <= 2e-4 * float(ab.abs().max() + 1e-30)
+
+
+@needs_cuda
+def test_render_service_equals_get_outputs_for_camera_and_survives_overflow():
+    """the captured-forward render service hands out, in order, exactly the maps of
+    model.get_outputs_for_camera (device maps and pinned host copies), and a view that does not fit the captured
+    intersection capacity is re-rendered after a re-capture instead of being delivered truncated."""
+    from dn_splatter_b200.render_service import ViewRenderer, _ForwardGraphs
+    from dn_splatter_b200.synthetic import ring_cameras
+
+    params, _ = scene_and_camera(4000, 160, 112)
+    m = _model(params)
+    W, H = 160, 112
+    cams = [_camera(c) for c in ring_cameras(7, W, H)]
+    keys = ("rgb", "depth", "normal", "surface_normal", "accumulation")
+    want = []
+    m.eval()
+    for c in cams:
+        out = m.get_outputs_for_camera(c)
+        want.append({k: out[k].clone() for k in keys})
+    m.train()
+    for to_host in (False, True):
+        r = ViewRenderer(m, keys=keys, to_host=to_host)
+        got = [(i, {k: v.clone() for k, v in d.items()}) for i, d in r.render(cams)]
+        assert [i for i, _ in got] == list(range(len(cams)))
+        for (i, d), w in zip(got, want):
+            for k in keys:
+                assert torch.equal(d[k].to("cuda"), w[k]), (to_host, i, k)
+        assert r.recaptures == 0 and m.training
+        # again through the same captured graphs (steady state)
+        for (i, d), w in zip(r.render(cams), want):
+            assert torch.equal(d["rgb"].to("cuda"), w["rgb"])
+    r = ViewRenderer(m, keys=keys, to_host=True)
+    r._graphs[(W, H)] = _ForwardGraphs(m, cams[0], keys, r.n_slots, capacity=4096)  # far too small: every view overflows it
+    got = [(i, {k: v.clone() for k, v in d.items()}) for i, d in r.render(cams)]
+    assert r.recaptures >= 1 and [i for i, _ in got] == list(range(len(cams)))
+    for (i, d), w in zip(got, want):
+        for k in keys:
+            assert torch.equal(d[k].to("cuda"), w[k]), (i, k)

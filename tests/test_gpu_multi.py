@@ -1,0 +1,90 @@
+"""Two-GPU tests (skipped on a single-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`):
+the gradient reduction fused into the Adam pass over NVLink peer memory (dnr_adam_step_reduce, parallel.PeerGradBucket)
+against the NCCL all-reduce + FusedAdam.step() pair on the same per-camera sharded training steps."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+needs_two = pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two CUDA devices")
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+
+    from dn_splatter_b200.cameras import Cameras
+    from dn_splatter_b200.dn_model import DNSplatterModelConfig
+    from dn_splatter_b200.losses import DepthLossType
+    from dn_splatter_b200.optim import FusedAdam
+    from dn_splatter_b200.synthetic import make_scene, ring_cameras
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    W, H, n = 160, 112, 6000
+    cams = [Cameras(c["c2w"][None], c["fx"], c["fy"], c["cx"], c["cy"], W, H, metadata={"cam_idx": i})
+            for i, c in enumerate(ring_cameras(8, W, H))]
+    g = torch.Generator().manual_seed(3)
+    batches = [{"image": (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8).to(dev),
+                "mono_depth": (2 + 6 * torch.rand(H, W, 1, generator=g)).to(dev),
+                "normal": (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8).to(dev)} for _ in range(8)]
+    out = {}
+    for mode in ("nccl", "peer"):
+        cfg = DNSplatterModelConfig(random_init=True, num_random=16, background_color="black", use_depth_loss=True,
+                                    depth_lambda=0.2, depth_loss_type=DepthLossType.EdgeAwareLogL1, ssim_lambda=0.2)
+        m = cfg.setup(device=dev)
+        m.load_gaussians(make_scene(n, seed=5))
+        m.step = 30000
+        m.train()
+        bucket = m.enable_flat_grads(peer=(mode == "peer"))
+        opt = FusedAdam.for_model(m)
+        for step in range(4):
+            v = step * world + rank  # per-camera sharding: every rank its own view
+            bucket.zero_()
+            o = m.get_outputs(cams[v % len(cams)])
+            ld = m.get_loss_dict(o, dict(batches[v % len(batches)]))
+            (ld["main_loss"] + ld["scale_reg"]).backward()
+            if mode == "nccl":
+                bucket.all_reduce()
+                opt.step()
+            else:
+                opt.step_reduce(bucket)
+        torch.cuda.synchronize()
+        out[mode] = {k: p.detach().cpu().clone() for k, p in m.gauss_params.items()}
+        dist.barrier()
+    # replicas must hold bit-identical parameters after peer-reduced steps
+    mine = torch.cat([out["peer"][k].reshape(-1) for k in sorted(out["peer"])]).to(dev)
+    theirs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(theirs, mine)
+    same = all(torch.equal(t, mine) for t in theirs)
+    if rank == 0:
+        ret.put((out, same))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@needs_two
+def test_peer_memory_reduce_adam_equals_allreduce_then_adam():
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out, same = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    assert same, "replicas diverged after the peer-memory reduction"
+    for k in out["nccl"]:
+        a, b = out["nccl"][k], out["peer"][k]
+        # two ranks: a + b is the same sum in either order -> the two paths agree to the last bit of every update
+        assert torch.equal(a, b) or float((a - b).abs().max()) <= 1e-6 * float(a.abs().max() + 1e-30), k

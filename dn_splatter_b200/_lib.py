@@ -51,7 +51,7 @@ class DnrAdamSeg(C.Structure):
     """Mirror of struct DnrAdamSeg (include/dnr.h)."""
 
     _fields_ = [("p", _p), ("g", _p), ("m", _p), ("v", _p), ("n", C.c_int64), ("lr", C.c_double), ("eps", C.c_double),
-                ("bc1", C.c_double), ("bc2_sqrt", C.c_double)]
+                ("bc1", C.c_double), ("bc2_sqrt", C.c_double), ("g_dense", _p)]
 
 
 PEER_MAX = 8
@@ -98,10 +98,20 @@ class _Counting:
         if k is None:
             return fn
 
+        debug = os.environ.get("DNR_DEBUG_CAPTURE") == "1"
+
         def call(*args):
             LAUNCHES["handwritten"] += k[0]
             LAUNCHES["cub"] += k[1]
-            return fn(*args)
+            rc = fn(*args)
+            if debug:  # name the C-ABI call that invalidates an ongoing stream capture
+                import torch
+
+                try:  # raises cudaErrorStreamCaptureInvalidated once the capture is broken
+                    torch.cuda.is_current_stream_capturing()
+                except Exception as exc:  # noqa: BLE001
+                    raise DnrError(f"stream capture invalidated by {name} (rc {rc}): {exc}") from exc
+            return rc
 
         self.__dict__[name] = call
         return call

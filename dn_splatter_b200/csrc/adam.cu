@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(256) peer_mask_kernel(const PeerDev P, int n, 
 
 struct AdamReduceLaunch {
   AdamLaunch adam;
+  const float* dense[DNR_ADAM_MAX_SEGS];  // rank-invariant gradient term per segment (or NULL)
+  float world_f;
   int64_t off[DNR_ADAM_MAX_SEGS];  // segment offset (floats) inside every rank's flat bucket
   int32_t width[DNR_ADAM_MAX_SEGS];  // floats per Gaussian in the segment
 };
@@ -111,6 +113,8 @@ __global__ void __launch_bounds__(256) adam_reduce_kernel(const AdamReduceLaunch
   const float step_size = s.step_size, bc2_sqrt = s.bc2_sqrt, eps = s.eps;
   const int64_t n = s.n, off = L.off[blockIdx.y];
   const int width = L.width[blockIdx.y];
+  const float* dense = L.dense[blockIdx.y];
+  const float wf = L.world_f;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n >> 2;  // segments start on 16-byte boundaries in every bucket (FlatGradBucket._padded)
   float4* p4 = reinterpret_cast<float4*>(s.p);
@@ -127,6 +131,10 @@ __global__ void __launch_bounds__(256) adam_reduce_kernel(const AdamReduceLaunch
         g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
       }
     }
+    if (dense != nullptr) {  // every rank holds the same values: world copies of it, none of them exchanged
+      const float4 d = reinterpret_cast<const float4*>(dense)[i];
+      g.x += wf * d.x; g.y += wf * d.y; g.z += wf * d.z; g.w += wf * d.w;
+    }
     float4 p = p4[i], m = m4[i], v = v4[i];
     adam_one(p.x, g.x, m.x, v.x, w1, b2, w2, step_size, bc2_sqrt, eps);
     adam_one(p.y, g.y, m.y, v.y, w1, b2, w2, step_size, bc2_sqrt, eps);
@@ -139,6 +147,7 @@ __global__ void __launch_bounds__(256) adam_reduce_kernel(const AdamReduceLaunch
     float g = 0.f;
     for (int k = 0; k < P.world; ++k)
       if ((mk >> k) & 1u) g += P.flat[k][off + i];
+    if (dense != nullptr) g += wf * dense[i];
     float p = s.p[i], m = s.m[i], v = s.v[i];
     adam_one(p, g, m, v, w1, b2, w2, step_size, bc2_sqrt, eps);
     s.p[i] = p; s.m[i] = m; s.v[i] = v;
@@ -179,13 +188,15 @@ extern "C" int dnr_adam_step_reduce(const DnrAdamSeg* segs, const int32_t* width
     P.flat[k] = peers->peer_flat[k];
     P.touched[k] = peers->peer_touched[k];
   }
+  L.world_f = (float)peers->world;
   const float* mine = peers->peer_flat[peers->rank];
   for (int i = 0; i < n_segs; ++i) {
     if (widths[i] <= 0 || segs[i].n % widths[i] != 0 || segs[i].n / widths[i] != peers->n_gauss) return DNR_E_SIZE;
     L.off[i] = segs[i].g - mine;  // the gradient segment lives at the same offset in every rank's bucket
     if (L.off[i] < 0 || (L.off[i] & 3) != 0) return DNR_E_SIZE;
-    if (((uintptr_t)segs[i].p | (uintptr_t)segs[i].m | (uintptr_t)segs[i].v) & 15) return DNR_E_SIZE;
+    if (((uintptr_t)segs[i].p | (uintptr_t)segs[i].m | (uintptr_t)segs[i].v | (uintptr_t)segs[i].g_dense) & 15) return DNR_E_SIZE;
     L.width[i] = widths[i];
+    L.dense[i] = segs[i].g_dense;
   }
   cudaStream_t s = (cudaStream_t)stream;
   const int n = peers->n_gauss;

@@ -36,9 +36,9 @@ __device__ __forceinline__ float ld_gt(const void* img, size_t idx) {
 
 // Horizontal pass: s_in[q][c][r][0..25] -> s_mid[q][c][r][0..15] for the NQ_OUT quantities `make` derives from the NQ_IN
 // loaded ones.  One work item = (channel, halo row, pair of adjacent output columns): 12 loaded values per input quantity.
-template <int NQ_IN, int NQ_OUT, typename Make>
-__device__ __forceinline__ void hpass(float (*s_in)[SS_C][SS_H][SS_P], float (*s_mid)[SS_C][SS_H][SS_T], int nc, int tid, Make make) {
-  const int items = nc * SS_H * (SS_T / 2);
+template <int NQ_IN, int NQ_OUT, int NC, typename Make>
+__device__ __forceinline__ void hpass(float (*s_in)[SS_C][SS_H][SS_P], float (*s_mid)[SS_C][SS_H][SS_T], int tid, Make make) {
+  constexpr int items = NC * SS_H * (SS_T / 2);
   for (int it = tid; it < items; it += SS_NT) {
     const int seg = it % (SS_T / 2), r = (it / (SS_T / 2)) % SS_H, c = it / ((SS_T / 2) * SS_H);
     float in[NQ_IN][12];
@@ -89,19 +89,22 @@ __device__ __forceinline__ void vpass(float (*s_mid)[SS_C][SS_H][SS_T], int c, i
 
 // sum_out[0] += SSIM over the interior; with L1: sum_out[1] += |x - y| over all pixels (the parent's photometric L1 shares
 // the pass: both values come from the same loads)
-template <bool U8, bool L1>
+// NC = channels this launch handles per CTA (compile time: the index arithmetic of the halo load and of the work-item
+// loops is mul-shift instead of runtime integer division, which cost a third of the round-2a kernel's instructions);
+// c0 = first channel.
+template <bool U8, bool L1, int NC>
 __global__ void __launch_bounds__(SS_NT) ssim_fwd_kernel(const float* __restrict__ x, const void* __restrict__ y, int H, int W,
-                                                        int C, float* __restrict__ dmaps, float* __restrict__ sum_out) {
+                                                        int C, int c0, float* __restrict__ dmaps, float* __restrict__ sum_out) {
   __shared__ __align__(16) float s_in[2][SS_C][SS_H][SS_P];
   __shared__ __align__(16) float s_mid[5][SS_C][SS_H][SS_T];
   __shared__ float red[SS_NT / 32];
   __shared__ float red_l1[SS_NT / 32];
   const int tid = threadIdx.x;
-  const int c0 = blockIdx.z * SS_C, nc = min(SS_C, C - c0);
+  constexpr int nc = NC;
   const int i0 = blockIdx.y * SS_T - SS_R, j0 = blockIdx.x * SS_T - SS_R;
   // halo load: consecutive threads walk (column, channel) of one image row -> contiguous global addresses
-  for (int e = tid; e < SS_H * SS_H * nc; e += SS_NT) {
-    const int c = e % nc, q = (e / nc) % SS_H, r = e / (nc * SS_H);
+  for (int e = tid; e < SS_H * SS_H * NC; e += SS_NT) {
+    const int c = e % NC, q = (e / NC) % SS_H, r = e / (NC * SS_H);
     const int i = i0 + r, j = j0 + q;
     float xv = 0.f, yv = 0.f;
     if (i >= 0 && i < H && j >= 0 && j < W) {
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(SS_NT) ssim_fwd_kernel(const float* __restrict
     s_in[1][c][r][q] = yv;
   }
   __syncthreads();
-  hpass<2, 5>(s_in, s_mid, nc, tid, [](const float* s, float* v) {
+  hpass<2, 5, NC>(s_in, s_mid, tid, [](const float* s, float* v) {
     v[0] = s[0]; v[1] = s[1]; v[2] = s[0] * s[0]; v[3] = s[1] * s[1]; v[4] = s[0] * s[1];
   });
   __syncthreads();
@@ -167,18 +170,18 @@ __global__ void photometric_finish_kernel(float* out, float lambda, float inv_co
 }
 
 // v_x = (*v_mean or 1) * (w_ssim * d(mean SSIM)/dx + w_l1 * d(mean |x - y|)/dx)
-template <bool U8>
+template <bool U8, int NC>
 __global__ void __launch_bounds__(SS_NT) ssim_bwd_kernel(const float* __restrict__ x, const void* __restrict__ y, int H, int W,
-                                                        int C, const float* __restrict__ dmaps, const float* v_mean,
+                                                        int C, int c0, const float* __restrict__ dmaps, const float* v_mean,
                                                         float w_ssim, float w_l1, float* __restrict__ v_x) {
   __shared__ __align__(16) float s_in[3][SS_C][SS_H][SS_P];
   __shared__ __align__(16) float s_mid[3][SS_C][SS_H][SS_T];
   const int tid = threadIdx.x;
-  const int c0 = blockIdx.z * SS_C, nc = min(SS_C, C - c0);
+  constexpr int nc = NC;
   const int i0 = blockIdx.y * SS_T - SS_R, j0 = blockIdx.x * SS_T - SS_R;
   const size_t n = (size_t)H * W * C;
-  for (int e = tid; e < SS_H * SS_H * nc; e += SS_NT) {
-    const int c = e % nc, q = (e / nc) % SS_H, r = e / (nc * SS_H);
+  for (int e = tid; e < SS_H * SS_H * NC; e += SS_NT) {
+    const int c = e % NC, q = (e / NC) % SS_H, r = e / (NC * SS_H);
     const int i = i0 + r, j = j0 + q;
     // the maps are zero outside the interior by construction (forward wrote zeros there); outside the image: zero
     float a = 0.f, b = 0.f, d = 0.f;
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(SS_NT) ssim_bwd_kernel(const float* __restrict
     s_in[0][c][r][q] = a; s_in[1][c][r][q] = b; s_in[2][c][r][q] = d;
   }
   __syncthreads();
-  hpass<3, 3>(s_in, s_mid, nc, tid, [](const float* s, float* v) { v[0] = s[0]; v[1] = s[1]; v[2] = s[2]; });
+  hpass<3, 3, NC>(s_in, s_mid, tid, [](const float* s, float* v) { v[0] = s[0]; v[1] = s[1]; v[2] = s[2]; });
   __syncthreads();
   if (tid < nc * SS_T * 4) {
     const int col = tid % SS_T, g = (tid / SS_T) % 4, c = tid / (SS_T * 4);
@@ -215,6 +218,35 @@ __global__ void __launch_bounds__(SS_NT) ssim_bwd_kernel(const float* __restrict
 
 }  // namespace
 
+// One launch per group of up to three channels (C = 3: a single launch).
+template <bool L1>
+static int launch_ssim_fwd(const float* pred, const void* gt, int gt_is_u8, int H, int W, int C, float* dmaps, float* out, cudaStream_t s) {
+  const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, 1);
+  for (int c0 = 0; c0 < C; c0 += SS_C) {
+    const int nc = C - c0 < SS_C ? C - c0 : SS_C;
+#define DNR_SSIM_FWD(U8, NC) ssim_fwd_kernel<U8, L1, NC><<<grid, SS_NT, 0, s>>>(pred, gt, H, W, C, c0, dmaps, out)
+    if (gt_is_u8) { if (nc == 3) DNR_SSIM_FWD(true, 3); else if (nc == 2) DNR_SSIM_FWD(true, 2); else DNR_SSIM_FWD(true, 1); }
+    else { if (nc == 3) DNR_SSIM_FWD(false, 3); else if (nc == 2) DNR_SSIM_FWD(false, 2); else DNR_SSIM_FWD(false, 1); }
+#undef DNR_SSIM_FWD
+    DNR_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+static int launch_ssim_bwd(const float* pred, const void* gt, int gt_is_u8, int H, int W, int C, const float* dmaps, const float* v,
+                           float w_ssim, float w_l1, float* v_pred, cudaStream_t s) {
+  const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, 1);
+  for (int c0 = 0; c0 < C; c0 += SS_C) {
+    const int nc = C - c0 < SS_C ? C - c0 : SS_C;
+#define DNR_SSIM_BWD(U8, NC) ssim_bwd_kernel<U8, NC><<<grid, SS_NT, 0, s>>>(pred, gt, H, W, C, c0, dmaps, v, w_ssim, w_l1, v_pred)
+    if (gt_is_u8) { if (nc == 3) DNR_SSIM_BWD(true, 3); else if (nc == 2) DNR_SSIM_BWD(true, 2); else DNR_SSIM_BWD(true, 1); }
+    else { if (nc == 3) DNR_SSIM_BWD(false, 3); else if (nc == 2) DNR_SSIM_BWD(false, 2); else DNR_SSIM_BWD(false, 1); }
+#undef DNR_SSIM_BWD
+    DNR_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
 // pred: [H,W,C] fp32; gt: [H,W,C] fp32, or uint8 scaled by 1/255 when gt_is_u8 != 0.  dmaps: [3,H,W,C] scratch kept for
 // the backward.  *sum_out (zeroed by the call) receives the SUM of the SSIM map over the interior; the caller divides by
 // (H-10)(W-10)C.
@@ -224,11 +256,7 @@ extern "C" int dnr_ssim_fwd_ex(const float* pred, const void* gt, int32_t gt_is_
   if (H <= 2 * SS_R || W <= 2 * SS_R || C <= 0) return DNR_E_SIZE;
   cudaStream_t s = (cudaStream_t)stream;
   DNR_CUDA(cudaMemsetAsync(sum_out, 0, sizeof(float), s));
-  const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, (C + SS_C - 1) / SS_C);
-  if (gt_is_u8) ssim_fwd_kernel<true, false><<<grid, SS_NT, 0, s>>>(pred, gt, H, W, C, dmaps, sum_out);
-  else ssim_fwd_kernel<false, false><<<grid, SS_NT, 0, s>>>(pred, gt, H, W, C, dmaps, sum_out);
-  DNR_CHECK_LAUNCH();
-  return 0;
+  return launch_ssim_fwd<false>(pred, gt, gt_is_u8, H, W, C, dmaps, sum_out, s);
 }
 
 // The whole photometric term of SplatfactoModel.get_loss_dict in one pass each way:
@@ -240,10 +268,7 @@ extern "C" int dnr_photometric_fwd(const float* pred, const void* gt, int32_t gt
   if (H <= 2 * SS_R || W <= 2 * SS_R || C <= 0) return DNR_E_SIZE;
   cudaStream_t s = (cudaStream_t)stream;
   DNR_CUDA(cudaMemsetAsync(out, 0, 3 * sizeof(float), s));
-  const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, (C + SS_C - 1) / SS_C);
-  if (gt_is_u8) ssim_fwd_kernel<true, true><<<grid, SS_NT, 0, s>>>(pred, gt, H, W, C, dmaps, out);
-  else ssim_fwd_kernel<false, true><<<grid, SS_NT, 0, s>>>(pred, gt, H, W, C, dmaps, out);
-  DNR_CHECK_LAUNCH();
+  if (const int rc = launch_ssim_fwd<true>(pred, gt, gt_is_u8, H, W, C, dmaps, out, s)) return rc;
   photometric_finish_kernel<<<1, 1, 0, s>>>(out, ssim_lambda, 1.0f / ((float)(H - 2 * SS_R) * (float)(W - 2 * SS_R) * (float)C),
                                             1.0f / ((float)H * (float)W * (float)C));
   DNR_CHECK_LAUNCH();
@@ -255,12 +280,7 @@ extern "C" int dnr_photometric_bwd(const float* pred, const void* gt, int32_t gt
                                    float ssim_lambda, const float* dmaps, const float* v_main, float* v_pred, void* stream) {
   if (!pred || !gt || !dmaps || !v_pred) return DNR_E_NULL;
   if (H <= 2 * SS_R || W <= 2 * SS_R || C <= 0) return DNR_E_SIZE;
-  const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, (C + SS_C - 1) / SS_C);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (gt_is_u8) ssim_bwd_kernel<true><<<grid, SS_NT, 0, s>>>(pred, gt, H, W, C, dmaps, v_main, -ssim_lambda, 1.0f - ssim_lambda, v_pred);
-  else ssim_bwd_kernel<false><<<grid, SS_NT, 0, s>>>(pred, gt, H, W, C, dmaps, v_main, -ssim_lambda, 1.0f - ssim_lambda, v_pred);
-  DNR_CHECK_LAUNCH();
-  return 0;
+  return launch_ssim_bwd(pred, gt, gt_is_u8, H, W, C, dmaps, v_main, -ssim_lambda, 1.0f - ssim_lambda, v_pred, (cudaStream_t)stream);
 }
 
 // v_pred[H,W,C] = (*v_mean or 1) * d(mean SSIM)/d(pred).
@@ -268,11 +288,7 @@ extern "C" int dnr_ssim_bwd_ex(const float* pred, const void* gt, int32_t gt_is_
                                const float* dmaps, const float* v_mean, float* v_pred, void* stream) {
   if (!pred || !gt || !dmaps || !v_pred) return DNR_E_NULL;
   if (H <= 2 * SS_R || W <= 2 * SS_R || C <= 0) return DNR_E_SIZE;
-  const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, (C + SS_C - 1) / SS_C);
-  if (gt_is_u8) ssim_bwd_kernel<true><<<grid, SS_NT, 0, (cudaStream_t)stream>>>(pred, gt, H, W, C, dmaps, v_mean, 1.0f, 0.0f, v_pred);
-  else ssim_bwd_kernel<false><<<grid, SS_NT, 0, (cudaStream_t)stream>>>(pred, gt, H, W, C, dmaps, v_mean, 1.0f, 0.0f, v_pred);
-  DNR_CHECK_LAUNCH();
-  return 0;
+  return launch_ssim_bwd(pred, gt, gt_is_u8, H, W, C, dmaps, v_mean, 1.0f, 0.0f, v_pred, (cudaStream_t)stream);
 }
 
 extern "C" int dnr_ssim_fwd(const float* pred, const float* gt, int32_t H, int32_t W, int32_t C, float* dmaps, float* sum_out,

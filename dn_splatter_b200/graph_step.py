@@ -95,23 +95,42 @@ class GraphedTrainStep:
                 self._eager(0)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
+        # capture_error_mode="thread_local": other threads of the process (NCCL's watchdog, the symmetric-memory runtime of a
+        # multi-rank job) keep making CUDA API calls while we capture; in the default "global" mode any of them invalidates
+        # the capture (cudaErrorStreamCaptureInvalidated, seen intermittently at 2 ranks)
         pool = None
         for slot in range(n_slots):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
                 self._eager(slot)
             pool = g.pool()
             self.graphs.append(g)
+
+    @staticmethod
+    def _capture_ok(where: str) -> None:
+        """DNR_DEBUG_CAPTURE=1: name the first stage after which an ongoing stream capture is no longer valid."""
+        import os
+
+        if os.environ.get("DNR_DEBUG_CAPTURE") != "1":
+            return
+        try:  # raises cudaErrorStreamCaptureInvalidated once the capture is broken
+            torch.cuda.is_current_stream_capturing()
+        except Exception as exc:  # noqa: BLE001
+            raise RuntimeError(f"stream capture invalidated during: {where}: {exc}") from exc
 
     def _eager(self, slot: int) -> None:
         m = self.model
         m.__dict__["_graph_cam"] = self.cam
         try:
             self.bucket.flat.zero_()
+            self._capture_ok("bucket zero")
             out = m.get_outputs(self._camera)
+            self._capture_ok("get_outputs")
             ld = m.get_loss_dict(out, dict(self.batches[slot]))
+            self._capture_ok("get_loss_dict")
             loss = ld["main_loss"] + ld["scale_reg"]
             loss.backward()
+            self._capture_ok("backward")
             self.losses[slot].copy_(loss.detach())
             self._count_dev[slot] = m.raster_out.info["n_isects_dev"]
         finally:

@@ -99,10 +99,18 @@ class PeerGradBucket(FlatGradBucket):
             self.views[n] = v
             off += self._padded(p.numel())
         self.mask = torch.zeros(tbytes, dtype=torch.uint8, device=dev)
+        # gradient terms that depend on the parameters alone are identical on every rank: they are kept out of the exchange
+        # (and out of the touched-row sparsity) in their own small buffers and added world-fold by the fused kernel
+        self.dense: Dict[str, Tensor] = {"scales": torch.zeros_like(ps["scales"])} if "scales" in ps else {}
         base = [int(x) for x in self._handle.buffer_ptrs]
         self.peer_flat = base
         self.peer_touched = [b + self._flat_bytes for b in base]
         assert self.peer_flat[self.rank] == self.flat.data_ptr()
+
+    def zero_(self) -> None:
+        super().zero_()
+        for t in self.dense.values():
+            t.zero_()
 
     def sink(self) -> Dict[str, Tensor]:
         out = dict(self.views)

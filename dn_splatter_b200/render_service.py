@@ -65,7 +65,7 @@ class _ForwardGraphs:
         self.graphs, self.maps, self.counts, pool = [], [], [], None
         for _ in range(self.n_slots):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
+            with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
                 maps, count = self._eager()
             pool = g.pool()
             self.graphs.append(g)

@@ -4,7 +4,7 @@ report the per-Gaussian gradient-scatter rate G * I_c / t against the measured H
 
     python scripts/bwd_microbench.py [--n 2000000] [--reps 10]
 
-(Written in round 1 after the GPU budget was spent: run and commit its output under profiles/ in round 2.)
+Results: profiles/bwd_microbench_r2*.jsonl.
 """
 import argparse
 import json
@@ -36,8 +36,9 @@ rows = []
 for scale_mult in (0.25, 0.5, 1.0, 2.0, 4.0):
     for op in ("0.1", "trained", "0.99"):
         p = {k: v.cuda().requires_grad_(True) for k, v in make_scene(args.n, seed=0, opacity_profile=op, scale_mult=scale_mult).items()}
+        stats = torch.zeros(4, dtype=torch.int64, device="cuda")
         out = dn_rasterize(p["means"], p["quats"], p["scales"], p["opacities"], p["features_dc"], p["features_rest"], vm, K, W, H,
-                           background=BACKGROUND, c2w=cam["c2w"])
+                           background=BACKGROUND, c2w=cam["c2w"], stats=stats)
         loss = sum((getattr(out, k) * w[k]).sum() for k in w) * 1e-3
         R.STAGE_EVENTS = []
         for _ in range(args.reps):
@@ -47,11 +48,9 @@ for scale_mult in (0.25, 0.5, 1.0, 2.0, 4.0):
         R.STAGE_EVENTS = None
         ms = sorted(t)[len(t) // 2]
         info = out.info
-        offs, last = info["tile_offsets"].long(), info["last_ids"].long()
-        pad_h, pad_w = (-H) % 16, (-W) % 16
-        lp = torch.nn.functional.pad(last, (0, pad_w, 0, pad_h), value=-1)
-        tmax = lp.view((H + pad_h) // 16, 16, (W + pad_w) // 16, 16).amax(dim=(1, 3)).reshape(-1)
-        i_c = int(torch.clamp(torch.minimum(tmax + 1, offs[1:]) - offs[:-1], min=0).sum())
+        # (tile, Gaussian) pairs the backward composites = list entries kept by the tile filter up to each tile's deepest
+        # last id (device counter stats[3], summed over the backward launches of this configuration)
+        i_c = int(stats[3]) // args.reps
         G = 60  # bytes of reduced gradient record per composited intersection (48 + 12 normals)
         rows.append({"scale_mult": scale_mult, "opacity": op, "n_isects": info["n_isects"], "n_composited": i_c,
                      "isects_per_gauss": info["n_isects"] / args.n, "raster_bwd_ms": ms,

@@ -1,16 +1,19 @@
 #!/bin/bash
-# Round 2: one `ncu --set full` capture for every hand-written kernel of the step that has none yet (round 1 captured
-# raster_fwd, raster_bwd, project_bwd).  About 1.5 GPU-minutes per kernel (bench setup dominates).
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/round2_ncu.sh'
-# then here:  for f in gpurun_out/prof_*_r2.ncu-rep; do python scripts/ncu_summary.py $f > profiles/$(basename ${f%.ncu-rep} | sed s/prof_//).txt; done
+# One `ncu --set full` capture per hand-written kernel of the training step (BASELINE north_star: "each kernel ships with an
+# ncu capture"), plus the launch list of one steady-state step.  ~1 GPU-minute per kernel (bench setup dominates).
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash scripts/round2_ncu.sh r2final'
+# then here:  python scripts/collect_profiles.py r2final
+TAG=${1:-r2final}
 mkdir -p gpurun_out
-# -s skips the launches of the setup pass (bench.py pre-visits all 200 views) so the captured launch is a warm step
-for k in project_fwd count emit pad offsets finalize_fwd loss_fwd loss_bwd; do
-  timeout 240 ncu --set full --clock-control none --import-source on -k regex:${k}_kernel -s 205 -c 1 \
-    -o gpurun_out/prof_${k}_r2 python bench.py --steps 2 --warmup 3 --gt-sets 2 --skip-cpu-baseline --skip-e2e --no-graph > /dev/null 2>&1
+B="python bench.py --steps 2 --warmup 3 --views 24 --gt-sets 2 --skip-cpu-baseline --skip-e2e --no-graph --epochs 0"
+# kernel regex : launches to skip (forward-only kernels also run in the 26 setup views)
+for spec in raster_bwd_kernel:4 raster_fwd_kernel:30 project_fwd_kernel:30 count_kernel:30 emit_kernel:30 offsets_kernel:30 \
+            finalize_fwd_kernel:30 loss_fwd_kernel:4 ssim_fwd_kernel:4 ssim_bwd_kernel:4 project_bwd_touched_kernel:4 \
+            adam_kernel:4 scale_loss_fwd_kernel:4; do
+  k=${spec%%:*}; skip=${spec##*:}
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:${k} -s ${skip} -c 1 -f -o gpurun_out/prof_${k%_kernel}_${TAG} $B > gpurun_out/ncu_${k}.log 2>&1
   echo "$k rc=$?"
 done
-# launch list of one eager step (per-kernel times; cold-cache, serialised: use the SHARES)
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r2.csv \
-  python bench.py --steps 2 --warmup 3 --gt-sets 2 --skip-cpu-baseline --skip-e2e --no-graph > gpurun_out/launches_r2.log 2>&1
-ls -la gpurun_out | grep r2
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 600 --csv --log-file gpurun_out/launches_${TAG}.csv $B > gpurun_out/launches_${TAG}.log 2>&1
+echo "launch list rc=$?"
+ls -la gpurun_out | grep ${TAG}

@@ -51,7 +51,7 @@ class DnrAdamSeg(C.Structure):
     """Mirror of struct DnrAdamSeg (include/dnr.h)."""
 
     _fields_ = [("p", _p), ("g", _p), ("m", _p), ("v", _p), ("n", C.c_int64), ("lr", C.c_double), ("eps", C.c_double),
-                ("bc1", C.c_double), ("bc2_sqrt", C.c_double), ("g_dense", _p)]
+                ("bc1", C.c_double), ("bc2_sqrt", C.c_double), ("dense", C.c_int64)]
 
 
 PEER_MAX = 8

@@ -15,7 +15,8 @@
 // non-zero only on the ranks whose view composited it (~10 % per view), so instead of an all-reduce of the dense bucket
 // (236 MB in and out per rank and step) each element's gradient is gathered straight from the peers that touched it —
 // sum over ranks in rank order, so every replica computes bit-identical updates — and consumed by the Adam update in the
-// same thread.  Inbound NVLink traffic is the touched rows only (~24 MB per peer at 1 M Gaussians / 1080p).
+// same thread.  Inbound NVLink traffic is the touched rows only (~24 MB per peer at 1 M Gaussians / 1080p), plus the few
+// segments flagged dense (the min-scale regulariser makes `scales` non-zero everywhere: 12 MB per peer).
 #include "common.cuh"
 
 namespace {
@@ -101,8 +102,7 @@ __global__ void __launch_bounds__(256) peer_mask_kernel(const PeerDev P, int n, 
 
 struct AdamReduceLaunch {
   AdamLaunch adam;
-  const float* dense[DNR_ADAM_MAX_SEGS];  // rank-invariant gradient term per segment (or NULL)
-  float world_f;
+  int dense[DNR_ADAM_MAX_SEGS];  // != 0: gather the segment's rows from every rank (see DnrAdamSeg.dense)
   int64_t off[DNR_ADAM_MAX_SEGS];  // segment offset (floats) inside every rank's flat bucket
   int32_t width[DNR_ADAM_MAX_SEGS];  // floats per Gaussian in the segment
 };
@@ -113,27 +113,24 @@ __global__ void __launch_bounds__(256) adam_reduce_kernel(const AdamReduceLaunch
   const float step_size = s.step_size, bc2_sqrt = s.bc2_sqrt, eps = s.eps;
   const int64_t n = s.n, off = L.off[blockIdx.y];
   const int width = L.width[blockIdx.y];
-  const float* dense = L.dense[blockIdx.y];
-  const float wf = L.world_f;
+  const uint32_t all_ranks = L.dense[blockIdx.y] ? ((1u << P.world) - 1u) : 0u;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n >> 2;  // segments start on 16-byte boundaries in every bucket (FlatGradBucket._padded)
   float4* p4 = reinterpret_cast<float4*>(s.p);
   float4* m4 = reinterpret_cast<float4*>(s.m);
   float4* v4 = reinterpret_cast<float4*>(s.v);
   for (int64_t i = tid; i < n4; i += stride) {
-    // rows that a rank did not touch are exactly zero in its bucket, so the union mask of the (at most two) Gaussians
-    // this float4 covers only decides which peers are worth reading; the sum runs in rank order on every replica
-    const uint32_t mk = (uint32_t)mask[(4 * i) / width] | (uint32_t)mask[(4 * i + 3) / width];
+    // rows that a rank did not touch are exactly zero in its bucket, so the union mask of the Gaussians this float4
+    // covers (up to four of them when width == 1) only decides which peers are worth reading; the sum runs in rank order
+    // on every replica
+    const uint32_t mk = all_ranks | (uint32_t)mask[(4 * i) / width] | (uint32_t)mask[(4 * i + 1) / width] |
+                        (uint32_t)mask[(4 * i + 2) / width] | (uint32_t)mask[(4 * i + 3) / width];
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = 0; k < P.world; ++k) {
       if ((mk >> k) & 1u) {
         const float4 t = reinterpret_cast<const float4*>(P.flat[k] + off)[i];
         g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
       }
-    }
-    if (dense != nullptr) {  // every rank holds the same values: world copies of it, none of them exchanged
-      const float4 d = reinterpret_cast<const float4*>(dense)[i];
-      g.x += wf * d.x; g.y += wf * d.y; g.z += wf * d.z; g.w += wf * d.w;
     }
     float4 p = p4[i], m = m4[i], v = v4[i];
     adam_one(p.x, g.x, m.x, v.x, w1, b2, w2, step_size, bc2_sqrt, eps);
@@ -143,11 +140,10 @@ __global__ void __launch_bounds__(256) adam_reduce_kernel(const AdamReduceLaunch
     p4[i] = p; m4[i] = m; v4[i] = v;
   }
   for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {  // tail
-    const uint32_t mk = mask[i / width];
+    const uint32_t mk = all_ranks | (uint32_t)mask[i / width];
     float g = 0.f;
     for (int k = 0; k < P.world; ++k)
       if ((mk >> k) & 1u) g += P.flat[k][off + i];
-    if (dense != nullptr) g += wf * dense[i];
     float p = s.p[i], m = s.m[i], v = s.v[i];
     adam_one(p, g, m, v, w1, b2, w2, step_size, bc2_sqrt, eps);
     s.p[i] = p; s.m[i] = m; s.v[i] = v;
@@ -188,15 +184,14 @@ extern "C" int dnr_adam_step_reduce(const DnrAdamSeg* segs, const int32_t* width
     P.flat[k] = peers->peer_flat[k];
     P.touched[k] = peers->peer_touched[k];
   }
-  L.world_f = (float)peers->world;
   const float* mine = peers->peer_flat[peers->rank];
   for (int i = 0; i < n_segs; ++i) {
     if (widths[i] <= 0 || segs[i].n % widths[i] != 0 || segs[i].n / widths[i] != peers->n_gauss) return DNR_E_SIZE;
     L.off[i] = segs[i].g - mine;  // the gradient segment lives at the same offset in every rank's bucket
     if (L.off[i] < 0 || (L.off[i] & 3) != 0) return DNR_E_SIZE;
-    if (((uintptr_t)segs[i].p | (uintptr_t)segs[i].m | (uintptr_t)segs[i].v | (uintptr_t)segs[i].g_dense) & 15) return DNR_E_SIZE;
+    if (((uintptr_t)segs[i].p | (uintptr_t)segs[i].m | (uintptr_t)segs[i].v) & 15) return DNR_E_SIZE;
     L.width[i] = widths[i];
-    L.dense[i] = segs[i].g_dense;
+    L.dense[i] = segs[i].dense != 0;
   }
   cudaStream_t s = (cudaStream_t)stream;
   const int n = peers->n_gauss;

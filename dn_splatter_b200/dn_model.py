@@ -231,9 +231,10 @@ class DNSplatterModel(_ModelBase):
         (parallel.PeerGradBucket)."""
         from .parallel import FlatGradBucket, PeerGradBucket
 
-        if peer and (self.config.regularization_strategy != "dn-splatter" or self.config.use_scale_regularization):
-            raise NotImplementedError("peer-memory gradient reduction needs every parameter-only (dense) gradient term routed "
-                                      "around the bucket; only DNRegularization's min-scale term is (use peer=False: NCCL all-reduce)")
+        if peer and (self.config.use_scale_regularization or self.config.use_sparse_loss):
+            raise NotImplementedError("peer-memory gradient reduction gathers only the rows of composited Gaussians, plus the "
+                                      "`scales` segment (min-scale regulariser); other parameter-only loss terms make more "
+                                      "segments dense: use peer=False (NCCL all-reduce)")
         self._bucket = PeerGradBucket(dict(self.gauss_params), group=group) if peer else FlatGradBucket(dict(self.gauss_params))
         return self._bucket
 
@@ -569,9 +570,6 @@ class DNSplatterModel(_ModelBase):
         if depth_gt is None and cfg.use_depth_loss:
             print("[dn_splatter_b200] use_depth_loss is True but the batch holds no depth maps")
         extra = {"scales": self.scales, "gt_img": gt_img}
-        dense = getattr(self._bucket, "dense", None) if torch.is_grad_enabled() else None
-        if dense and cfg.regularization_strategy == "dn-splatter":
-            extra["scale_grad_sink"] = dense.get("scales")  # peer bucket: the rank-invariant term stays out of the exchange
         if cfg.regularization_strategy == "dn-splatter":
             reg = self.regularization_strategy(pred_depth=depth_out, gt_depth=depth_gt, pred_normal=pred_normal,
                                                gt_normal=gt_normal, **extra)

@@ -107,9 +107,7 @@ class FusedAdam(torch.optim.Optimizer):
             arr[i].p, arr[i].g, arr[i].m, arr[i].v = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
             arr[i].n, arr[i].lr, arr[i].eps, arr[i].bc1, arr[i].bc2_sqrt = p.numel(), lr, eps, bc1, bc2s
             widths[i] = p.numel() // bucket.n_gauss
-            for name, dense in bucket.dense.items():  # rank-invariant gradient term of this parameter (min-scale loss)
-                if bucket.params[name] is p:
-                    arr[i].g_dense = dense.data_ptr()
+            arr[i].dense = int(any(bucket.params[name] is p for name in bucket.dense_params))
         pr = L.DnrPeerReduce()
         pr.world, pr.rank, pr.n_gauss = bucket.world, bucket.rank, bucket.n_gauss
         for k in range(bucket.world):

@@ -99,18 +99,13 @@ class PeerGradBucket(FlatGradBucket):
             self.views[n] = v
             off += self._padded(p.numel())
         self.mask = torch.zeros(tbytes, dtype=torch.uint8, device=dev)
-        # gradient terms that depend on the parameters alone are identical on every rank: they are kept out of the exchange
-        # (and out of the touched-row sparsity) in their own small buffers and added world-fold by the fused kernel
-        self.dense: Dict[str, Tensor] = {"scales": torch.zeros_like(ps["scales"])} if "scales" in ps else {}
+        # parameters whose gradient is non-zero for every Gaussian on every rank (a loss term that depends on the parameters
+        # alone: DNRegularization's min-scale term on `scales`): their segment is gathered from all ranks, not by `touched`
+        self.dense_params = {"scales"} & set(ps)
         base = [int(x) for x in self._handle.buffer_ptrs]
         self.peer_flat = base
         self.peer_touched = [b + self._flat_bytes for b in base]
         assert self.peer_flat[self.rank] == self.flat.data_ptr()
-
-    def zero_(self) -> None:
-        super().zero_()
-        for t in self.dense.values():
-            t.zero_()
 
     def sink(self) -> Dict[str, Tensor]:
         out = dict(self.views)

@@ -135,9 +135,7 @@ class _ScaleLoss(torch.autograd.Function):
     """mean_i min_k exp(scales[i,k]) (reference regularization_strategy.py:195-199)."""
 
     @staticmethod
-    def forward(ctx, scales, sink=None):
-        """`sink` [N,3]: write the (dense, rank-invariant) gradient there instead of handing it to autograd — multi-GPU
-        peer reduction keeps such terms out of the exchanged bucket (parallel.PeerGradBucket.dense)."""
+    def forward(ctx, scales):
         lib = L.load()
         if scales.device.type != "cuda":
             raise L.DnrError("scale loss: CUDA tensor required (no CPU path)")
@@ -145,7 +143,6 @@ class _ScaleLoss(torch.autograd.Function):
         out = torch.empty(1, dtype=torch.float32, device=s.device)
         L.check(lib.dnr_scale_loss_fwd(s.data_ptr(), s.shape[0], out.data_ptr(), _stream()), "dnr_scale_loss_fwd")
         ctx.s = s
-        ctx.sink = sink
         ctx.fwd_stream = torch.cuda.current_stream()
         return out[0].clone()
 
@@ -159,10 +156,10 @@ class _ScaleLoss(torch.autograd.Function):
         lib = L.load()
         s = ctx.s
         v = v.detach().float().contiguous()
-        g = ctx.sink if ctx.sink is not None else torch.empty_like(s)
+        g = torch.empty_like(s)
         L.check(lib.dnr_scale_loss_bwd(s.data_ptr(), s.shape[0], v.data_ptr(), g.data_ptr(), _stream()),
                 "dnr_scale_loss_bwd")
-        return (None, None) if ctx.sink is not None else (g, None)
+        return g
 
 
 class FusedL1(torch.autograd.Function):
@@ -313,8 +310,8 @@ class RegularizationStrategy(nn.Module):
     def forward(self, **kwargs):
         return self.get_loss(**kwargs)
 
-    def get_scale_loss(self, scales, sink=None):
-        return _ScaleLoss.apply(scales, sink)
+    def get_scale_loss(self, scales):
+        return _ScaleLoss.apply(scales)
 
 
 class DNRegularization(RegularizationStrategy):
@@ -368,7 +365,7 @@ class DNRegularization(RegularizationStrategy):
                 loss = loss + self.get_depth_loss(pred_depth, gt_depth, **kwargs)
             if with_normal:
                 loss = loss + self.get_normal_loss(pred_normal, gt_normal, **kwargs)
-        return loss + self.get_scale_loss(scales=kwargs["scales"], sink=kwargs.get("scale_grad_sink"))
+        return loss + self.get_scale_loss(scales=kwargs["scales"])
 
     # --- the reference's per-term methods, kept callable (torch path for non-fused depth types) ---
     def get_depth_loss(self, pred_depth, gt_depth, **kwargs):

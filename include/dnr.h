@@ -263,9 +263,9 @@ typedef struct DnrAdamSeg {
   float* v;       /* [n] exp_avg_sq, updated in place */
   int64_t n;
   double lr, eps, bc1, bc2_sqrt; /* doubles: rounded to fp32 exactly where torch.optim.Adam rounds them */
-  const float* g_dense; /* [n] or NULL — dnr_adam_step_reduce only: a gradient term that is IDENTICAL on every rank (it depends
-                           on the parameters alone, e.g. the min-scale regulariser) and therefore stays out of the exchange:
-                           the reduced gradient is sum_k rows_k + world * g_dense */
+  int64_t dense; /* dnr_adam_step_reduce only: != 0 -> every rank's rows of this segment are gathered, not just the rows of
+                    the ranks that touched the Gaussian (a gradient term that depends on the parameters alone, e.g. the
+                    min-scale regulariser, makes the whole segment non-zero on every rank) */
 } DnrAdamSeg;
 int dnr_adam_step(const DnrAdamSeg* segs /* HOST array */, int32_t n_segs, double beta1, double beta2, void* stream);
 

@@ -66,7 +66,7 @@ def cpu_proxy():
 
     class ScaleProxy:
         @staticmethod
-        def apply(scales, sink=None):
+        def apply(scales):
             return torch.exp(scales).min(dim=1, keepdim=True)[0].mean()
 
     class DNProxy:

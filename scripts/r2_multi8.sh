@@ -1,6 +1,7 @@
 #!/bin/bash
 # round 2, 8-GPU call: C2 at N=8 (peer-memory reduce fused into Adam vs dense NCCL all-reduce), N=4, and C4 (6M Gaussians, 1440p)
 mkdir -p gpurun_out
+timeout 200 python -m pytest tests/test_gpu_multi.py -q -m gpu -x > gpurun_out/r2m8_tests.log 2>&1; echo "multi tests rc=$?"; grep -v "^$" gpurun_out/r2m8_tests.log | grep -iv "warning" | tail -4 | cut -c1-300
 run() { # tag nproc extra...
   tag=$1; np=$2; shift 2
   timeout 330 python -m torch.distributed.run --nnodes=1 --nproc-per-node $np --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $np --steps 20 --warmup 5 --skip-cpu-baseline "$@" > gpurun_out/r2m8_$tag.json 2> gpurun_out/r2m8_$tag.err

@@ -38,7 +38,7 @@ def _worker(rank, world, port, n_views, ret):
                 bucket.views[k] += g  # what the rasterizer's grad-sink / autograd accumulation does
     bucket.all_reduce()
     if rank == 0:
-        ret.put({k: params[k].grad.clone() for k in bucket.names})
+        ret.put({k: params[k].grad.numpy().copy() for k in bucket.names})  # numpy: pickled by value, no fd hand-off
     dist.barrier()
     dist.destroy_process_group()
 
@@ -65,7 +65,7 @@ def test_two_rank_gradient_equals_single_rank():
             if k in want:
                 want[k] += g
     for k in GRAD_PARAMS:
-        torch.testing.assert_close(got[k], want[k], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(torch.from_numpy(got[k]), want[k], rtol=1e-6, atol=1e-6)
     assert sorted(shard_views(5, 0, 2) + shard_views(5, 1, 2)) == list(range(5))
 
 
@@ -80,7 +80,7 @@ def _stats_worker(rank, world, port, ret):
         st.after_train(absgrad, radii, (48, 64))
     st.all_reduce_()
     if rank == 1:
-        ret.put((st.xys_grad_norm.clone(), st.vis_counts.clone(), st.max_2Dsize.clone()))
+        ret.put(tuple(t.numpy().copy() for t in (st.xys_grad_norm, st.vis_counts, st.max_2Dsize)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -111,6 +111,7 @@ def test_two_rank_densification_statistics_equal_single_rank():
     st = DensifyState()
     for v in range(6):
         st.after_train(*_fake_view_stats(v), (48, 64))
+    got = [torch.from_numpy(a) for a in got]
     torch.testing.assert_close(got[0], st.xys_grad_norm, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(got[1], st.vis_counts)
     torch.testing.assert_close(got[2], st.max_2Dsize)
@@ -129,7 +130,7 @@ def _warmup_worker(rank, world, port, ret):
         st.after_train(absgrad, radii, (48, 64))
         if step > 0 and step % 2 == 0:
             if st.all_reduce_before_refinement(step, warmup):
-                consumed.append((step, st.xys_grad_norm.clone(), st.vis_counts.clone(), st.max_2Dsize.clone()))
+                consumed.append((step, st.xys_grad_norm.numpy().copy(), st.vis_counts.numpy().copy(), st.max_2Dsize.numpy().copy()))
                 st.reset()
     if rank == 0:
         ret.put(consumed)
@@ -161,6 +162,6 @@ def test_statistics_are_not_re_reduced_during_warmup():
     for step in range(7):  # steps 0..6 on both ranks feed the first refinement
         for r in range(world):
             st.after_train(*_fake_view_stats(step * world + r), (48, 64))
-    torch.testing.assert_close(got[0][1], st.xys_grad_norm, rtol=1e-6, atol=1e-7)
-    torch.testing.assert_close(got[0][2], st.vis_counts)
-    torch.testing.assert_close(got[0][3], st.max_2Dsize)
+    torch.testing.assert_close(torch.from_numpy(got[0][1]), st.xys_grad_norm, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(torch.from_numpy(got[0][2]), st.vis_counts)
+    torch.testing.assert_close(torch.from_numpy(got[0][3]), st.max_2Dsize)

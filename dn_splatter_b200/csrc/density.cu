@@ -9,8 +9,8 @@
 // One thread per sample (dnr_density) or per pixel ray (dnr_ray_densities: the 16 neighbours are gathered once and
 // reused for the 21 samples).  Precise expf / division: this is an export-time path compared value by value.
 //
-// STATUS: written in round 1 after the GPU budget was spent — compiled, the algorithm pinned on the CPU
-// (oracle/sugar_ref.py vs goldens from the reference's own functions), NOT yet run on a GPU (tests/test_gpu_sugar.py).
+// The algorithm is pinned on the CPU (oracle/sugar_ref.py vs goldens from the reference's own functions) and the kernel
+// against that restatement on the GPU (tests/test_gpu_sugar.py).
 #include "common.cuh"
 
 namespace {

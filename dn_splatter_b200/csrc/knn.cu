@@ -10,8 +10,8 @@
 // coordinate -> cell map is monotone per axis, two points whose cells differ by D along an axis are at least (D-1) cells
 // apart, so after shell r everything unvisited is >= r * cell away: the search stops once the K-th distance <= r * cell.
 //
-// STATUS: written in round 1 after the GPU budget was spent — compiled, algorithm pinned on the CPU by a numpy mirror
-// against sklearn (tests/test_knn_grid_cpu.py), NOT yet run on a GPU (opt-in test: tests/test_gpu_sugar.py).
+// Pinned on the CPU by a numpy mirror against sklearn (tests/test_knn_grid_cpu.py) and on the GPU against a brute-force
+// fp64 distance matrix (tests/test_gpu_sugar.py).
 #include <cub/cub.cuh>
 
 #include "common.cuh"

@@ -551,7 +551,7 @@ __device__ __forceinline__ void project_bwd_gauss(const DnrArgs& a, int i, int n
 
 // The 180 B/Gaussian SH-gradient rows are staged in shared memory (stride 45 words: conflict-free) and written
 // by the whole CTA as one contiguous, coalesced stream instead of 45 strided 4-byte stores per thread.
-// COMPACT (experimental, DNR_FLAG_COMPACT_BWD): slot s of the grid handles Gaussian depth_order[s]; the visible ones
+// COMPACT (DNR_FLAG_COMPACT_BWD, kept for A/B; the touched-flag kernel below is the default): slot s of the grid handles Gaussian depth_order[s]; the visible ones
 // come first in that order, so full CTAs do useful work and the tail CTAs leave after one load.  Rows are then
 // scattered, hence accumulate-only.
 template <bool NORMALS, bool COMPACT>

@@ -6,9 +6,10 @@ learning rate per group, eps 1e-15, an exponential schedule on `means`) and nerf
 `state[p] = {"step", "exp_avg", "exp_avg_sq"}`, so densification's moment surgery (densify._resize_adam_state) and
 checkpointing work unchanged — but `step()` is a single `dnr_adam_step` launch over all groups.
 
-EXPERIMENTAL in round 1: the update rule is pinned against torch.optim.Adam on the CPU through
-`reference_step` (tests/test_fused_adam_cpu.py); the kernel has not run on a GPU yet
-(opt-in test: DNR_TEST_EXPERIMENTAL=1 pytest -m gpu -k fused_adam).
+The update rule is pinned against torch.optim.Adam on the CPU through `reference_step` (tests/test_fused_adam_cpu.py)
+and the kernel against torch.optim.Adam on the GPU (tests/test_gpu_model.py); it runs at the HBM roofline (0.27 ms for
+59 M floats).  `step_reduce(bucket)` is the multi-GPU form: the gradient sum over ranks happens inside the same kernel,
+read from the peers' buckets over NVLink (parallel.PeerGradBucket, tests/test_gpu_multi.py).
 """
 from __future__ import annotations
 

@@ -7,9 +7,8 @@ sklearn on the CPU) and the per-ray density evaluation (`dnr_ray_densities`: 21 
 of 2M-sample torch passes that materialise [2M,16,3,3] tensors); the level-crossing search and the normal modes are
 small gather ops on the device.  No CPU path.
 
-EXPERIMENTAL in round 1: written after the GPU budget was spent.  The algorithms are pinned on the CPU (oracle/sugar_ref.py
-against goldens from the reference's own functions; a numpy mirror of the grid search against sklearn); the kernels
-themselves still need their GPU run (tests/test_gpu_sugar.py, opt-in).
+The algorithms are pinned on the CPU (oracle/sugar_ref.py against goldens from the reference's own functions; a numpy
+mirror of the grid search against sklearn) and the kernels against those on the GPU (tests/test_gpu_sugar.py).
 """
 from __future__ import annotations
 

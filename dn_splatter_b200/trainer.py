@@ -19,7 +19,7 @@ class Trainer:
         self.model, self.next_train, self.max_steps = model, next_train, max_steps
         self.groups = optimizer_groups(max_steps)
         self.fused = None
-        if fused_adam:  # EXPERIMENTAL (round 1): all groups in one dnr_adam_step launch, see optim.py
+        if fused_adam:  # all groups in one dnr_adam_step launch, see optim.py
             from .optim import FusedAdam
 
             self.fused = FusedAdam.for_model(model, self.groups)

@@ -49,7 +49,7 @@ extern "C" {
 #define DNR_FLAG_ANTIALIASED 2u /* rasterize_mode == "antialiased": opacity *= compensation */
 #define DNR_FLAG_NORMALS 4u     /* predict_normals: render the per-Gaussian normal channels */
 #define DNR_FLAG_ACCUMULATE 8u  /* project_bwd adds into the parameter-gradient buffers */
-#define DNR_FLAG_COMPACT_BWD 64u /* EXPERIMENTAL (not validated on a GPU yet): project_bwd walks the depth-sorted index
+#define DNR_FLAG_COMPACT_BWD 64u /* project_bwd walks the depth-sorted index (validated, but slower than DNR_FLAG_TOUCHED_BWD: kept for A/B)
                                     (a->depth_order), so only visible Gaussians occupy lanes; needs DNR_FLAG_ACCUMULATE */
 #define DNR_FLAG_HOST_CAMERA 32u /* camera passed by value in host_cam[] (no device reads, no H2D copy) */
 #define DNR_FLAG_EXACT_LISTS 16u /* parity mode: emit gsplat's full bbox intersection lists (no precise-hit cull) */
@@ -254,7 +254,7 @@ int dnr_photometric_bwd(const float* pred, const void* gt, int32_t gt_is_u8, int
 /* One-launch Adam over all Gaussian parameter groups: replaces the per-group torch.optim.Adam instances of
  * dn_splatter/dn_config.py:29-68 (lr per group, eps 1e-15; betas (0.9, 0.999), no weight decay, no amsgrad).
  * bc1 = 1 - beta1^t and bc2_sqrt = sqrt(1 - beta2^t) are computed by the host for each group's own step count t.
- * EXPERIMENTAL in round 1 (opt-in through optim.FusedAdam). */
+ * Python surface: optim.FusedAdam. */
 #define DNR_ADAM_MAX_SEGS 16
 typedef struct DnrAdamSeg {
   float* p;       /* [n] parameters, updated in place */
@@ -288,7 +288,7 @@ typedef struct DnrPeerReduce {
 int dnr_adam_step_reduce(const DnrAdamSeg* segs /* HOST array */, const int32_t* widths /* HOST array */, int32_t n_segs,
                          double beta1, double beta2, const DnrPeerReduce* peers /* HOST struct */, void* stream);
 
-/* ---- SuGaR-style queries (EXPERIMENTAL in round 1: opt-in through dn_splatter_b200.sugar) ----
+/* ---- SuGaR-style queries (Python surface: dn_splatter_b200.sugar) ----
  * Grid-hash k-NN: replaces sklearn behind dn_splatter/utils/knn.py:29-43 (knn_sk) and nerfstudio's k_nearest_sklearn
  * (dn_model.py:187).  The host chooses the grid; points outside it are clamped into the border cells (still exact). */
 typedef struct DnrKnnGrid {

@@ -107,12 +107,16 @@ struct AdamReduceLaunch {
   int32_t width[DNR_ADAM_MAX_SEGS];  // floats per Gaussian in the segment
 };
 
-__global__ void __launch_bounds__(256) adam_reduce_kernel(const AdamReduceLaunch L, const PeerDev P, const uint8_t* __restrict__ mask) {
+// WORLD = the rank count rounded up to 2 / 4 / 8: the peer loop unrolls completely, every peer's float4 is requested with
+// a predicated load BEFORE the first one is consumed (a thread otherwise pays one NVLink round trip, ~2 us, per touching
+// rank in turn), and the local p / m / v loads are already in flight behind them.  Bits of ranks >= world are never set.
+template <int WORLD>
+__global__ void __launch_bounds__(256, WORLD > 4 ? 3 : 4) adam_reduce_kernel(const AdamReduceLaunch L, const PeerDev P, const uint8_t* __restrict__ mask) {
   const AdamSegDev& s = L.adam.seg[blockIdx.y];
   const float w1 = L.adam.w1, b2 = L.adam.beta2, w2 = L.adam.w2;
   const float step_size = s.step_size, bc2_sqrt = s.bc2_sqrt, eps = s.eps;
   const int64_t n = s.n, off = L.off[blockIdx.y];
-  const int width = L.width[blockIdx.y];
+  const uint32_t width = (uint32_t)L.width[blockIdx.y];
   const uint32_t all_ranks = L.dense[blockIdx.y] ? ((1u << P.world) - 1u) : 0u;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n >> 2;  // segments start on 16-byte boundaries in every bucket (FlatGradBucket._padded)
@@ -122,17 +126,22 @@ __global__ void __launch_bounds__(256) adam_reduce_kernel(const AdamReduceLaunch
   for (int64_t i = tid; i < n4; i += stride) {
     // rows that a rank did not touch are exactly zero in its bucket, so the union mask of the Gaussians this float4
     // covers (up to four of them when width == 1) only decides which peers are worth reading; the sum runs in rank order
-    // on every replica
-    const uint32_t mk = all_ranks | (uint32_t)mask[(4 * i) / width] | (uint32_t)mask[(4 * i + 1) / width] |
-                        (uint32_t)mask[(4 * i + 2) / width] | (uint32_t)mask[(4 * i + 3) / width];
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < P.world; ++k) {
-      if ((mk >> k) & 1u) {
-        const float4 t = reinterpret_cast<const float4*>(P.flat[k] + off)[i];
-        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
-      }
-    }
+    // on every replica.  n < 2^32 (checked by the host): 32-bit divisions.
+    const uint32_t e = (uint32_t)(i << 2);
+    const uint32_t mk = all_ranks | (uint32_t)mask[e / width] | (uint32_t)mask[(e + 1u) / width] |
+                        (uint32_t)mask[(e + 2u) / width] | (uint32_t)mask[(e + 3u) / width];
     float4 p = p4[i], m = m4[i], v = v4[i];
+    float4 t[WORLD];
+#pragma unroll
+    for (int k = 0; k < WORLD; ++k) {
+      t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((mk >> k) & 1u) t[k] = reinterpret_cast<const float4*>(P.flat[k] + off)[i];
+    }
+    float4 g = t[0];
+#pragma unroll
+    for (int k = 1; k < WORLD; ++k) {  // x + 0 == x: the zeros of untouched ranks do not change the rank-ordered sum
+      g.x += t[k].x; g.y += t[k].y; g.z += t[k].z; g.w += t[k].w;
+    }
     adam_one(p.x, g.x, m.x, v.x, w1, b2, w2, step_size, bc2_sqrt, eps);
     adam_one(p.y, g.y, m.y, v.y, w1, b2, w2, step_size, bc2_sqrt, eps);
     adam_one(p.z, g.z, m.z, v.z, w1, b2, w2, step_size, bc2_sqrt, eps);
@@ -140,7 +149,7 @@ __global__ void __launch_bounds__(256) adam_reduce_kernel(const AdamReduceLaunch
     p4[i] = p; m4[i] = m; v4[i] = v;
   }
   for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {  // tail
-    const uint32_t mk = all_ranks | (uint32_t)mask[i / width];
+    const uint32_t mk = all_ranks | (uint32_t)mask[(uint32_t)i / width];
     float g = 0.f;
     for (int k = 0; k < P.world; ++k)
       if ((mk >> k) & 1u) g += P.flat[k][off + i];
@@ -187,6 +196,7 @@ extern "C" int dnr_adam_step_reduce(const DnrAdamSeg* segs, const int32_t* width
   const float* mine = peers->peer_flat[peers->rank];
   for (int i = 0; i < n_segs; ++i) {
     if (widths[i] <= 0 || segs[i].n % widths[i] != 0 || segs[i].n / widths[i] != peers->n_gauss) return DNR_E_SIZE;
+    if (segs[i].n >= ((int64_t)1 << 32)) return DNR_E_SIZE;  // the kernel indexes a segment's elements with 32 bits
     L.off[i] = segs[i].g - mine;  // the gradient segment lives at the same offset in every rank's bucket
     if (L.off[i] < 0 || (L.off[i] & 3) != 0) return DNR_E_SIZE;
     if (((uintptr_t)segs[i].p | (uintptr_t)segs[i].m | (uintptr_t)segs[i].v) & 15) return DNR_E_SIZE;
@@ -200,7 +210,10 @@ extern "C" int dnr_adam_step_reduce(const DnrAdamSeg* segs, const int32_t* width
   int64_t blocks = (longest / 4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  adam_reduce_kernel<<<dim3((unsigned)blocks, (unsigned)n_segs), 256, 0, s>>>(L, P, peers->mask);
+  const dim3 grid((unsigned)blocks, (unsigned)n_segs);
+  if (peers->world <= 2) adam_reduce_kernel<2><<<grid, 256, 0, s>>>(L, P, peers->mask);
+  else if (peers->world <= 4) adam_reduce_kernel<4><<<grid, 256, 0, s>>>(L, P, peers->mask);
+  else adam_reduce_kernel<8><<<grid, 256, 0, s>>>(L, P, peers->mask);
   DNR_CHECK_LAUNCH();
   return 0;
 }

@@ -7,9 +7,9 @@ TAG=${1:-r2final}
 mkdir -p gpurun_out
 B="python bench.py --steps 2 --warmup 3 --views 24 --gt-sets 2 --skip-cpu-baseline --skip-e2e --no-graph --epochs 0"
 # kernel regex : launches to skip (forward-only kernels also run in the 26 setup views)
-for spec in raster_bwd_kernel:4 raster_fwd_kernel:30 project_fwd_kernel:30 count_kernel:30 emit_kernel:30 offsets_kernel:30 \
+for spec in raster_bwd_kernel:4 raster_fwd_kernel:30 project_fwd_kernel:30 count_kernel:30 emit_kernel:30 \
             finalize_fwd_kernel:30 loss_fwd_kernel:4 ssim_fwd_kernel:4 ssim_bwd_kernel:4 project_bwd_touched_kernel:4 \
-            adam_kernel:4 scale_loss_fwd_kernel:4; do
+            adam_kernel:4; do
   k=${spec%%:*}; skip=${spec##*:}
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:${k} -s ${skip} -c 1 -f -o gpurun_out/prof_${k%_kernel}_${TAG} $B > gpurun_out/ncu_${k}.log 2>&1
   echo "$k rc=$?"

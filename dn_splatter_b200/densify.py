@@ -227,7 +227,10 @@ def _replace_params(model, optimizers: Dict[str, torch.optim.Optimizer], new_dat
             _resize_adam_state(opt, old, new, state_fn)
         model.gauss_params[name] = new
     if getattr(model, "_bucket", None) is not None:
-        model.enable_flat_grads()  # the flat gradient bucket must follow the new parameter set
+        # the flat gradient bucket must follow the new parameter set; a peer bucket is re-allocated in symmetric memory (a
+        # collective: every rank refines at the same step with identical decisions, see Trainer)
+        peer, group = getattr(model, "_bucket_mode", (False, None))
+        model.enable_flat_grads(peer=peer, group=group)
 
 
 def build_optimizers(model, groups: Optional[Dict[str, Dict]] = None) -> Dict[str, torch.optim.Optimizer]:

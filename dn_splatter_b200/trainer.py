@@ -15,7 +15,7 @@ from .dn_config import MAX_NUM_ITERATIONS, optimizer_groups
 
 class Trainer:
     def __init__(self, model, next_train: Callable[[int], tuple], max_steps: int = MAX_NUM_ITERATIONS,
-                 world_size: int = 1, seed: int = 0, fused_adam: bool = False):
+                 world_size: int = 1, seed: int = 0, fused_adam: bool = False, peer_reduce: bool = False):
         self.model, self.next_train, self.max_steps = model, next_train, max_steps
         self.groups = optimizer_groups(max_steps)
         self.fused = None
@@ -26,7 +26,12 @@ class Trainer:
             self.optimizers: Dict[str, torch.optim.Optimizer] = self.fused.as_dict(model)
         else:
             self.optimizers = build_optimizers(model, self.groups)
-        self.bucket = model.enable_flat_grads()
+        # peer_reduce: the gradient sum over ranks happens inside the Adam kernel over NVLink peer memory
+        # (optim.FusedAdam.step_reduce) instead of an NCCL all-reduce of the dense bucket followed by the step
+        self.peer_reduce = bool(peer_reduce) and world_size > 1
+        if self.peer_reduce and self.fused is None:
+            raise ValueError("peer_reduce needs fused_adam=True (the reduction is part of dnr_adam_step_reduce)")
+        self.bucket = model.enable_flat_grads(peer=self.peer_reduce)
         self.world_size = world_size
         self.generator = torch.Generator().manual_seed(seed)  # identical on every rank: identical split samples
         self.step = 0
@@ -42,7 +47,7 @@ class Trainer:
         loss_dict = m.get_loss_dict(outputs, batch)
         loss = loss_dict["main_loss"] + loss_dict["scale_reg"]
         loss.backward()
-        if self.world_size > 1:
+        if self.world_size > 1 and not self.peer_reduce:
             self.bucket.all_reduce()
         for name, opt in self.optimizers.items():
             g = self.groups[name]
@@ -52,7 +57,9 @@ class Trainer:
                         pg["lr"] = exponential_lr(g["lr"], g["lr_final"], step, g["max_steps"])
             if self.fused is None:
                 opt.step()
-        if self.fused is not None:
+        if self.peer_reduce:
+            self.fused.step_reduce(self.bucket)
+        elif self.fused is not None:
             self.fused.step()
         m.after_train(step)
         info: Optional[Dict[str, int]] = None

@@ -76,8 +76,7 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-@needs_two
-def test_peer_memory_reduce_adam_equals_allreduce_then_adam():
+def _run_two(worker):
     world = 2
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -85,7 +84,7 @@ def test_peer_memory_reduce_adam_equals_allreduce_then_adam():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     import queue
@@ -101,10 +100,80 @@ def test_peer_memory_reduce_adam_equals_allreduce_then_adam():
                 for p in procs:
                     p.kill()
                 raise AssertionError(f"worker failed (exit codes {[p.exitcode for p in procs]}) or timed out")
-    worst, same, touched_frac = got
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    return got
+
+
+def _trainer_worker(rank, world, port, ret):
+    """Trainer(fused_adam=True, peer_reduce=True) through a refinement: per-camera sharding, statistics reduced before the
+    refinement, the peer bucket re-allocated in symmetric memory for the new Gaussian count."""
+    import torch.distributed as dist
+
+    from dn_splatter_b200.cameras import Cameras
+    from dn_splatter_b200.dn_model import DNSplatterModelConfig
+    from dn_splatter_b200.losses import DepthLossType
+    from dn_splatter_b200.parallel import PeerGradBucket
+    from dn_splatter_b200.synthetic import make_scene, ring_cameras
+    from dn_splatter_b200.trainer import Trainer
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    W, H, n_views = 96, 64, 8
+    cams = [Cameras(c["c2w"][None], c["fx"], c["fy"], c["cx"], c["cy"], W, H, metadata={"cam_idx": i})
+            for i, c in enumerate(ring_cameras(n_views, W, H))]
+    g = torch.Generator().manual_seed(3)
+    batches = [{"image": (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8).to(dev),
+                "mono_depth": (2 + 6 * torch.rand(H, W, 1, generator=g)).to(dev),
+                "normal": (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8).to(dev)} for _ in range(n_views)]
+    cfg = DNSplatterModelConfig(random_init=True, num_random=16, background_color="black", use_depth_loss=True, depth_lambda=0.2,
+                                depth_loss_type=DepthLossType.EdgeAwareLogL1, ssim_lambda=0.2, warmup_length=5, refine_every=4,
+                                densify_grad_thresh=1e-5, sh_degree_interval=1)
+    m = cfg.setup(device=dev, num_train_data=n_views)
+    m.load_gaussians(make_scene(1500, seed=4))
+    m.num_train_data = n_views
+
+    def next_train(step):  # per-camera sharding: rank r renders views {i : i mod world == r}
+        v = (step * world + rank) % n_views
+        return cams[v], dict(batches[v])
+
+    tr = Trainer(m, next_train, max_steps=200, world_size=world, fused_adam=True, peer_reduce=True)
+    counts, finite = [], True
+    for _ in range(11):
+        out = tr.train_iteration()
+        finite &= bool(torch.isfinite(out["loss"]))
+        counts.append(m.num_points)
+    torch.cuda.synchronize()
+    names = sorted(k for k in m.gauss_params if k != "normals")
+    mine = torch.cat([m.gauss_params[k].detach().reshape(-1) for k in names])
+    n_all = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(n_all, torch.tensor([mine.numel()], dtype=torch.int64, device=dev))
+    same = len({int(x) for x in n_all}) == 1
+    if same:
+        theirs = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(theirs, mine)
+        same = all(torch.equal(t, mine) for t in theirs)
+    if rank == 0:
+        ret.put((counts, finite, same, isinstance(m._bucket, PeerGradBucket), m._bucket.n_gauss == m.num_points))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@needs_two
+def test_trainer_peer_reduce_survives_refinement_with_identical_replicas():
+    counts, finite, same, is_peer, follows = _run_two(_trainer_worker)
+    assert finite
+    assert len(set(counts)) > 1, counts  # steps 8: past the warm-up, the (absurdly low) threshold densifies
+    assert is_peer and follows, "the refinement must re-create the bucket in peer mode for the new Gaussian count"
+    assert same, "replicas diverged"
+
+
+@needs_two
+def test_peer_memory_reduce_adam_equals_allreduce_then_adam():
+    worst, same, touched_frac = _run_two(_worker)
     assert same, "replicas diverged after the peer-memory reduction"
     assert 0.0 < touched_frac < 0.9, touched_frac  # the exchange is sparse: only composited Gaussians travel
     for k, (mx, frac) in worst.items():

@@ -142,7 +142,7 @@ def _trainer_worker(rank, world, port, ret):
 
     tr = Trainer(m, next_train, max_steps=200, world_size=world, fused_adam=True, peer_reduce=True)
     counts, finite = [], True
-    for _ in range(11):
+    for _ in range(18):
         out = tr.train_iteration()
         finite &= bool(torch.isfinite(out["loss"]))
         counts.append(m.num_points)
@@ -166,7 +166,9 @@ def _trainer_worker(rank, world, port, ret):
 def test_trainer_peer_reduce_survives_refinement_with_identical_replicas():
     counts, finite, same, is_peer, follows = _run_two(_trainer_worker)
     assert finite
-    assert len(set(counts)) > 1, counts  # steps 8: past the warm-up, the (absurdly low) threshold densifies
+    # step 16 is the first refine boundary past the warm-up with step % reset > num_train_data + refine_every
+    # (dn_model.py:299-303); the (absurdly low) threshold then densifies
+    assert len(set(counts)) > 1, counts
     assert is_peer and follows, "the refinement must re-create the bucket in peer mode for the new Gaussian count"
     assert same, "replicas diverged"
 

@@ -96,7 +96,7 @@ def _run_two(worker):
             got = q.get(timeout=2)
         except queue.Empty:
             dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
-            if dead or time.time() - t0 > 240:
+            if dead or time.time() - t0 > 420:
                 for p in procs:
                     p.kill()
                 raise AssertionError(f"worker failed (exit codes {[p.exitcode for p in procs]}) or timed out")

@@ -79,3 +79,50 @@ def test_too_many_tensors():
     ps = [{"params": [torch.nn.Parameter(torch.zeros(2))]} for _ in range(17)]
     with pytest.raises(ValueError):
         FusedAdam(ps)
+
+
+def _peer_gather_mirror(rows, touched, width):
+    """numpy mirror of csrc/adam.cu adam_reduce_kernel's gather: `rows[k]` = rank k's flat gradient segment (rows of
+    untouched Gaussians are exactly zero), `touched[k]` = its per-Gaussian flags.  Per float4 i the union of the masks of
+    the Gaussians its four elements belong to selects the ranks to read; the sum runs in rank order."""
+    import numpy as np
+
+    world, n = len(rows), rows[0].size
+    mask = np.zeros(touched[0].size, dtype=np.uint32)
+    for k in range(world):
+        mask |= (touched[k] != 0).astype(np.uint32) << k
+    out = np.zeros(n, dtype=np.float32)
+    for i in range(n // 4):
+        e = 4 * i
+        mk = mask[e // width] | mask[(e + 1) // width] | mask[(e + 2) // width] | mask[(e + 3) // width]
+        g = np.zeros(4, dtype=np.float32)
+        for k in range(world):
+            if (mk >> k) & 1:
+                g = g + rows[k][e:e + 4]
+        out[e:e + 4] = g
+    for j in range(n // 4 * 4, n):
+        for k in range(world):
+            if (mask[j // width] >> k) & 1:
+                out[j] += rows[k][j]
+    return out
+
+
+@pytest.mark.parametrize("width", [1, 3, 4, 45])
+def test_masked_peer_gather_equals_the_dense_sum(width):
+    """The exchange of dnr_adam_step_reduce reads only the rows of ranks that touched a Gaussian; because untouched rows are
+    zero that must equal the dense sum over ranks bit for bit — also where one float4 spans several Gaussians (width 1: four
+    of them; width 3 / 45: rows straddle float4 boundaries)."""
+    import numpy as np
+
+    rng = np.random.default_rng(width)
+    world, n_gauss = 3, 37
+    touched = [(rng.random(n_gauss) < 0.35).astype(np.uint8) for _ in range(world)]
+    rows = [(rng.standard_normal((n_gauss, width)).astype(np.float32) * touched[k][:, None]).reshape(-1) for k in range(world)]
+    dense = np.zeros(n_gauss * width, dtype=np.float32)
+    for k in range(world):
+        dense = dense + rows[k]
+    got = _peer_gather_mirror(rows, touched, width)
+    assert np.array_equal(got, dense)
+    # the per-Gaussian mask alone (the bug this guards against) would drop neighbours' rows inside a shared float4
+    if width == 1:
+        assert any(touched[k][g] and not touched[k][g - g % 4] for k in range(world) for g in range(n_gauss))

@@ -165,3 +165,75 @@ def test_statistics_are_not_re_reduced_during_warmup():
     torch.testing.assert_close(torch.from_numpy(got[0][1]), st.xys_grad_norm, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(torch.from_numpy(got[0][2]), st.vis_counts)
     torch.testing.assert_close(torch.from_numpy(got[0][3]), st.max_2Dsize)
+
+
+def _trainer_worker(rank, world, port, ret):
+    """Trainer(world_size=2) on the CPU proxy: per-camera sharding, flat all-reduce (gloo), statistics reduced before the
+    refinement, identical split samples — the replicas must hold identical parameters after a densification."""
+    from dn_splatter_b200.cameras import Cameras
+    from dn_splatter_b200.dn_model import DNSplatterModelConfig
+    from dn_splatter_b200.losses import DepthLossType
+    from dn_splatter_b200.synthetic import make_scene, ring_cameras
+    from dn_splatter_b200.trainer import Trainer
+    from tests.cpu_proxy import cpu_proxy
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    W, H, n_views = 40, 32, 4
+    cams = [Cameras(c["c2w"][None], c["fx"], c["fy"], c["cx"], c["cy"], W, H, metadata={"cam_idx": i})
+            for i, c in enumerate(ring_cameras(n_views, W, H))]
+    g = torch.Generator().manual_seed(3)
+    batches = [{"image": (torch.rand(H, W, 3, generator=g) * 255).to(torch.uint8),
+                "mono_depth": 2 + 6 * torch.rand(H, W, 1, generator=g),
+                "normal": torch.rand(H, W, 3, generator=g)} for _ in range(n_views)]
+    cfg = DNSplatterModelConfig(random_init=True, num_random=16, background_color="black", use_depth_loss=True, depth_lambda=0.2,
+                                depth_loss_type=DepthLossType.LogL1, ssim_lambda=0.0, warmup_length=3, refine_every=3,
+                                densify_grad_thresh=1e-6, sh_degree_interval=1)
+    with cpu_proxy():
+        m = cfg.setup(device="cpu", num_train_data=2)
+        m.load_gaussians(make_scene(60, seed=4))
+        m.num_train_data = 2
+
+        def next_train(step):  # rank r renders views {i : i mod world == r}
+            v = (step * world + rank) % n_views
+            return cams[v], dict(batches[v])
+
+        tr = Trainer(m, next_train, max_steps=100, world_size=world)
+        counts = []
+        for _ in range(8):  # boundary 6: past the warm-up and step % reset > num_train_data + refine_every -> densifies
+            out = tr.train_iteration()
+            assert torch.isfinite(out["loss"])
+            counts.append(m.num_points)
+    names = sorted(k for k in m.gauss_params if k != "normals")
+    mine = torch.cat([m.gauss_params[k].detach().reshape(-1) for k in names])
+    sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([mine.numel()]))
+    same = len({int(s) for s in sizes}) == 1
+    if same:
+        theirs = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(theirs, mine)
+        same = all(torch.equal(t, mine) for t in theirs)
+    if rank == 0:
+        ret.put((counts, same))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_trainer_keeps_replicas_identical_through_a_refinement():
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_trainer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    counts, same = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert len(set(counts)) > 1, counts
+    assert same, "replicas diverged"
